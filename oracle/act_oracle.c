@@ -1,0 +1,1305 @@
+/*
+ * act_oracle.c -- CPU ORACLE for the issuer-side hot path of anonymous-credit-tokens.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (anonymous-credit-tokens_b200/csrc, libact_b200.so) never links or calls this file.
+ *
+ * It is a plain-C restatement of the reference crate's algorithm (crate v0.2.1):
+ *   src/lib.rs:291-354   Params::new / hash_to_ristretto
+ *   src/lib.rs:463-487   PreIssuance::request            (fixture generation)
+ *   src/lib.rs:528-562   PreIssuance::to_credit_token
+ *   src/lib.rs:621-663   PrivateKey::issue
+ *   src/lib.rs:781-869   PrivateKey::refund
+ *   src/lib.rs:902-915,972-1152  bits_of / CreditToken::prove_spend (fixture generation)
+ *   src/lib.rs:1217-1253 PreRefund::to_credit_token
+ *   src/transcript.rs:29-155  Transcript
+ *   src/cbor.rs:62-91    decode_point / decode_scalar semantics
+ *
+ * The arithmetic the reference takes from un-vendored crates is restated from the
+ * published algorithms: curve25519-dalek 4.1.3 (RFC 9496 ristretto255 encode/decode/
+ * one-way map; radix-16 constant-time variable-base and basepoint-table scalar
+ * multiplication; Montgomery mod-l scalars) and blake3 1.8.2 (BLAKE3 spec).
+ *
+ * PARITY PINNING: the reference's own tests hold no known-answer vectors (all OsRng), and
+ * no Rust toolchain exists in this image, so parity with the crate is pinned indirectly:
+ * this oracle is checked (tests/test_oracle_*.py) against RFC 9496 Appendix A vectors,
+ * BLAKE3 via the independent python `blake3` package, an independent libsodium
+ * ristretto255 + python big-int restatement of the whole issue->spend->refund trip, and
+ * the SURVEY.md Appendix C provisional golden trip.  "parity unpinned by the reference's
+ * own tests" -- see DESIGN.md.
+ *
+ * Representation here is deliberately different from the GPU code (5x51-bit limbs with
+ * unsigned __int128 products vs. 8x32-bit limbs on the device) so that the two
+ * implementations do not share bugs.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <stdlib.h>
+#include <pthread.h>
+#include <time.h>
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef unsigned __int128 u128;
+
+#define ACT_L 128 /* src/lib.rs:116 */
+
+/* ------------------------------------------------------------------------------------
+ * GF(2^255-19), 5 x 51-bit limbs
+ * ---------------------------------------------------------------------------------- */
+typedef struct { u64 v[5]; } fe;
+#define M51 ((1ULL << 51) - 1)
+
+static void fe_0(fe *h) { memset(h, 0, sizeof *h); }
+static void fe_1(fe *h) { fe_0(h); h->v[0] = 1; }
+
+static u64 load64(const u8 *s) {
+    u64 r = 0;
+    for (int i = 7; i >= 0; i--) r = (r << 8) | s[i];
+    return r;
+}
+static void store64(u8 *s, u64 x) {
+    for (int i = 0; i < 8; i++) { s[i] = (u8)x; x >>= 8; }
+}
+
+/* dalek FieldElement::from_bytes: bit 255 is ignored */
+static void fe_frombytes(fe *h, const u8 s[32]) {
+    u64 x0 = load64(s), x1 = load64(s + 8), x2 = load64(s + 16), x3 = load64(s + 24);
+    h->v[0] = x0 & M51;
+    h->v[1] = ((x0 >> 51) | (x1 << 13)) & M51;
+    h->v[2] = ((x1 >> 38) | (x2 << 26)) & M51;
+    h->v[3] = ((x2 >> 25) | (x3 << 39)) & M51;
+    h->v[4] = (x3 >> 12) & M51;
+}
+
+static void fe_weak_reduce(fe *h) {
+    u64 c0 = h->v[0] >> 51, c1 = h->v[1] >> 51, c2 = h->v[2] >> 51, c3 = h->v[3] >> 51,
+        c4 = h->v[4] >> 51;
+    h->v[0] &= M51; h->v[1] &= M51; h->v[2] &= M51; h->v[3] &= M51; h->v[4] &= M51;
+    h->v[0] += c4 * 19; h->v[1] += c0; h->v[2] += c1; h->v[3] += c2; h->v[4] += c3;
+}
+
+/* canonical little-endian encoding */
+static void fe_tobytes(u8 s[32], const fe *f) {
+    fe t = *f;
+    fe_weak_reduce(&t);
+    fe_weak_reduce(&t);
+    u64 q = (t.v[0] + 19) >> 51;
+    q = (t.v[1] + q) >> 51;
+    q = (t.v[2] + q) >> 51;
+    q = (t.v[3] + q) >> 51;
+    q = (t.v[4] + q) >> 51;
+    t.v[0] += 19 * q;
+    t.v[1] += t.v[0] >> 51; t.v[0] &= M51;
+    t.v[2] += t.v[1] >> 51; t.v[1] &= M51;
+    t.v[3] += t.v[2] >> 51; t.v[2] &= M51;
+    t.v[4] += t.v[3] >> 51; t.v[3] &= M51;
+    t.v[4] &= M51;
+    store64(s, t.v[0] | (t.v[1] << 51));
+    store64(s + 8, (t.v[1] >> 13) | (t.v[2] << 38));
+    store64(s + 16, (t.v[2] >> 26) | (t.v[3] << 25));
+    store64(s + 24, (t.v[3] >> 39) | (t.v[4] << 12));
+}
+
+static void fe_add(fe *h, const fe *f, const fe *g) {
+    for (int i = 0; i < 5; i++) h->v[i] = f->v[i] + g->v[i];
+    fe_weak_reduce(h);
+}
+/* h = f - g : add 16p first so limbs never go negative */
+static void fe_sub(fe *h, const fe *f, const fe *g) {
+    h->v[0] = (f->v[0] + 36028797018963664ULL) - g->v[0];
+    h->v[1] = (f->v[1] + 36028797018963952ULL) - g->v[1];
+    h->v[2] = (f->v[2] + 36028797018963952ULL) - g->v[2];
+    h->v[3] = (f->v[3] + 36028797018963952ULL) - g->v[3];
+    h->v[4] = (f->v[4] + 36028797018963952ULL) - g->v[4];
+    fe_weak_reduce(h);
+}
+static void fe_neg(fe *h, const fe *f) { fe z; fe_0(&z); fe_sub(h, &z, f); }
+
+static void fe_mul(fe *h, const fe *f, const fe *g) {
+    const u64 a0 = f->v[0], a1 = f->v[1], a2 = f->v[2], a3 = f->v[3], a4 = f->v[4];
+    const u64 b0 = g->v[0], b1 = g->v[1], b2 = g->v[2], b3 = g->v[3], b4 = g->v[4];
+    const u64 b1_19 = b1 * 19, b2_19 = b2 * 19, b3_19 = b3 * 19, b4_19 = b4 * 19;
+    u128 c0 = (u128)a0 * b0 + (u128)a4 * b1_19 + (u128)a3 * b2_19 + (u128)a2 * b3_19 + (u128)a1 * b4_19;
+    u128 c1 = (u128)a1 * b0 + (u128)a0 * b1 + (u128)a4 * b2_19 + (u128)a3 * b3_19 + (u128)a2 * b4_19;
+    u128 c2 = (u128)a2 * b0 + (u128)a1 * b1 + (u128)a0 * b2 + (u128)a4 * b3_19 + (u128)a3 * b4_19;
+    u128 c3 = (u128)a3 * b0 + (u128)a2 * b1 + (u128)a1 * b2 + (u128)a0 * b3 + (u128)a4 * b4_19;
+    u128 c4 = (u128)a4 * b0 + (u128)a3 * b1 + (u128)a2 * b2 + (u128)a1 * b3 + (u128)a0 * b4;
+    c1 += (u64)(c0 >> 51); u64 r0 = (u64)c0 & M51;
+    c2 += (u64)(c1 >> 51); u64 r1 = (u64)c1 & M51;
+    c3 += (u64)(c2 >> 51); u64 r2 = (u64)c2 & M51;
+    c4 += (u64)(c3 >> 51); u64 r3 = (u64)c3 & M51;
+    u64 carry = (u64)(c4 >> 51); u64 r4 = (u64)c4 & M51;
+    r0 += carry * 19;
+    r1 += r0 >> 51; r0 &= M51;
+    h->v[0] = r0; h->v[1] = r1; h->v[2] = r2; h->v[3] = r3; h->v[4] = r4;
+}
+
+static void fe_sq(fe *h, const fe *f) {
+    const u64 a0 = f->v[0], a1 = f->v[1], a2 = f->v[2], a3 = f->v[3], a4 = f->v[4];
+    const u64 a3_19 = 19 * a3, a4_19 = 19 * a4;
+    u128 c0 = (u128)a0 * a0 + 2 * ((u128)a1 * a4_19 + (u128)a2 * a3_19);
+    u128 c1 = (u128)a3 * a3_19 + 2 * ((u128)a0 * a1 + (u128)a2 * a4_19);
+    u128 c2 = (u128)a1 * a1 + 2 * ((u128)a0 * a2 + (u128)a4 * a3_19);
+    u128 c3 = (u128)a4 * a4_19 + 2 * ((u128)a0 * a3 + (u128)a1 * a2);
+    u128 c4 = (u128)a2 * a2 + 2 * ((u128)a0 * a4 + (u128)a1 * a3);
+    c1 += (u64)(c0 >> 51); u64 r0 = (u64)c0 & M51;
+    c2 += (u64)(c1 >> 51); u64 r1 = (u64)c1 & M51;
+    c3 += (u64)(c2 >> 51); u64 r2 = (u64)c2 & M51;
+    c4 += (u64)(c3 >> 51); u64 r3 = (u64)c3 & M51;
+    u64 carry = (u64)(c4 >> 51); u64 r4 = (u64)c4 & M51;
+    r0 += carry * 19;
+    r1 += r0 >> 51; r0 &= M51;
+    h->v[0] = r0; h->v[1] = r1; h->v[2] = r2; h->v[3] = r3; h->v[4] = r4;
+}
+static void fe_sqn(fe *h, const fe *f, int n) {
+    fe_sq(h, f);
+    for (int i = 1; i < n; i++) fe_sq(h, h);
+}
+
+/* z^(2^250-1) and z^11, the common prefix of invert and pow22523 */
+static void fe_pow22501(fe *t250, fe *z11, const fe *z) {
+    fe t0, t1, t2, t3;
+    fe_sq(&t0, z);            /* 2 */
+    fe_sqn(&t1, &t0, 2);      /* 8 */
+    fe_mul(&t1, z, &t1);      /* 9 */
+    fe_mul(&t0, &t0, &t1);    /* 11 */
+    fe_sq(&t2, &t0);          /* 22 */
+    fe_mul(&t1, &t1, &t2);    /* 31 = 2^5-1 */
+    fe_sqn(&t2, &t1, 5); fe_mul(&t1, &t2, &t1);     /* 2^10-1 */
+    fe_sqn(&t2, &t1, 10); fe_mul(&t2, &t2, &t1);    /* 2^20-1 */
+    fe_sqn(&t3, &t2, 20); fe_mul(&t2, &t3, &t2);    /* 2^40-1 */
+    fe_sqn(&t2, &t2, 10); fe_mul(&t1, &t2, &t1);    /* 2^50-1 */
+    fe_sqn(&t2, &t1, 50); fe_mul(&t2, &t2, &t1);    /* 2^100-1 */
+    fe_sqn(&t3, &t2, 100); fe_mul(&t2, &t3, &t2);   /* 2^200-1 */
+    fe_sqn(&t2, &t2, 50); fe_mul(&t1, &t2, &t1);    /* 2^250-1 */
+    *t250 = t1; *z11 = t0;
+}
+static void fe_invert(fe *out, const fe *z) {
+    fe t, z11;
+    fe_pow22501(&t, &z11, z);
+    fe_sqn(&t, &t, 5);
+    fe_mul(out, &t, &z11); /* z^(2^255-21) */
+}
+static void fe_pow22523(fe *out, const fe *z) {
+    fe t, z11;
+    fe_pow22501(&t, &z11, z);
+    fe_sqn(&t, &t, 2);
+    fe_mul(out, &t, z); /* z^(2^252-3) */
+}
+static int fe_is_negative(const fe *f) { u8 s[32]; fe_tobytes(s, f); return s[0] & 1; }
+static int fe_is_zero(const fe *f) {
+    u8 s[32]; fe_tobytes(s, f);
+    u8 r = 0; for (int i = 0; i < 32; i++) r |= s[i];
+    return r == 0;
+}
+static int fe_eq(const fe *a, const fe *b) {
+    u8 s[32], t[32]; fe_tobytes(s, a); fe_tobytes(t, b);
+    return memcmp(s, t, 32) == 0;
+}
+static void fe_cmov(fe *f, const fe *g, int b) {
+    u64 m = (u64)0 - (u64)(b & 1);
+    for (int i = 0; i < 5; i++) f->v[i] ^= m & (f->v[i] ^ g->v[i]);
+}
+static void fe_cneg(fe *f, int b) { fe n; fe_neg(&n, f); fe_cmov(f, &n, b); }
+
+/* constants (RFC 9496 section 4.1; verified algebraically in oracle_selftest) */
+static fe FE_D, FE_D2, FE_SQRT_M1, FE_SQRT_AD_MINUS_ONE, FE_INVSQRT_A_MINUS_D, FE_ONE_MINUS_D_SQ,
+    FE_D_MINUS_ONE_SQ, FE_ONE;
+
+static void hex2bytes(u8 *out, const char *hex, int n) {
+    for (int i = 0; i < n; i++) {
+        int hi = hex[2 * i], lo = hex[2 * i + 1];
+        hi = hi <= '9' ? hi - '0' : hi - 'a' + 10;
+        lo = lo <= '9' ? lo - '0' : lo - 'a' + 10;
+        out[i] = (u8)(hi << 4 | lo);
+    }
+}
+static void fe_fromhex(fe *f, const char *hex) { u8 b[32]; hex2bytes(b, hex, 32); fe_frombytes(f, b); }
+
+/* RFC 9496 4.2 SQRT_RATIO_M1 as dalek's FieldElement::sqrt_ratio_i. returns was_square */
+static int fe_sqrt_ratio_i(fe *r_out, const fe *u, const fe *v) {
+    fe v3, v7, r, check, t, neg_u, neg_u_i, r_prime;
+    fe_sq(&t, v); fe_mul(&v3, &t, v);
+    fe_sq(&t, &v3); fe_mul(&v7, &t, v);
+    fe_mul(&t, u, &v7); fe_pow22523(&t, &t);
+    fe_mul(&r, u, &v3); fe_mul(&r, &r, &t);
+    fe_sq(&t, &r); fe_mul(&check, v, &t);
+    fe_neg(&neg_u, u);
+    fe_mul(&neg_u_i, &neg_u, &FE_SQRT_M1);
+    int correct_sign = fe_eq(&check, u);
+    int flipped_sign = fe_eq(&check, &neg_u);
+    int flipped_sign_i = fe_eq(&check, &neg_u_i);
+    fe_mul(&r_prime, &FE_SQRT_M1, &r);
+    fe_cmov(&r, &r_prime, flipped_sign | flipped_sign_i);
+    fe_cneg(&r, fe_is_negative(&r));
+    *r_out = r;
+    return correct_sign | flipped_sign;
+}
+
+/* ------------------------------------------------------------------------------------
+ * scalars mod l = 2^252 + 27742317777372353535851937790883648493, 4x64 Montgomery
+ * ---------------------------------------------------------------------------------- */
+typedef struct { u64 v[4]; } sc;
+static const u64 SC_L[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0ULL, 0x1000000000000000ULL};
+static u64 SC_LFACTOR;   /* -l^{-1} mod 2^64 */
+static sc SC_R, SC_RR;   /* 2^256 mod l, 2^512 mod l */
+
+static int sc_geq_l(const u64 a[4]) {
+    for (int i = 3; i >= 0; i--) {
+        if (a[i] > SC_L[i]) return 1;
+        if (a[i] < SC_L[i]) return 0;
+    }
+    return 1;
+}
+static void sc_sub_l(u64 a[4]) {
+    u128 b = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 t = (u128)a[i] - SC_L[i] - (u64)b;
+        a[i] = (u64)t; b = (t >> 64) & 1;
+    }
+}
+static void sc_zero(sc *a) { memset(a, 0, sizeof *a); }
+static void sc_from_u64(sc *a, u64 x) { sc_zero(a); a->v[0] = x; }
+static void sc_add(sc *r, const sc *a, const sc *b) {
+    u128 c = 0; u64 t[4];
+    for (int i = 0; i < 4; i++) { c += (u128)a->v[i] + b->v[i]; t[i] = (u64)c; c >>= 64; }
+    /* a,b < l < 2^253 so no carry out */
+    if (sc_geq_l(t)) sc_sub_l(t);
+    memcpy(r->v, t, 32);
+}
+static void sc_neg(sc *r, const sc *a) {
+    u64 t[4]; u128 b = 0; int z = (a->v[0] | a->v[1] | a->v[2] | a->v[3]) == 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)SC_L[i] - a->v[i] - (u64)b;
+        t[i] = (u64)d; b = (d >> 64) & 1;
+    }
+    if (z) memset(t, 0, 32);
+    memcpy(r->v, t, 32);
+}
+static void sc_sub(sc *r, const sc *a, const sc *b) { sc n; sc_neg(&n, b); sc_add(r, a, &n); }
+/* a*b*2^-256 mod l; needs a*b < l*2^256 */
+static void sc_montmul(sc *r, const sc *a, const sc *b) {
+    u64 t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)t[j] + (u128)a->v[j] * b->v[i];
+            t[j] = (u64)c; c >>= 64;
+        }
+        c += t[4]; t[4] = (u64)c; t[5] = (u64)(c >> 64);
+        u64 m = t[0] * SC_LFACTOR;
+        c = (u128)t[0] + (u128)m * SC_L[0]; c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)t[j] + (u128)m * SC_L[j];
+            t[j - 1] = (u64)c; c >>= 64;
+        }
+        c += t[4]; t[3] = (u64)c; t[4] = t[5] + (u64)(c >> 64);
+    }
+    /* result < 2l, fits 256 bits as l < 2^253 */
+    if (t[4] || sc_geq_l(t)) sc_sub_l(t);
+    memcpy(r->v, t, 32);
+}
+static void sc_mul(sc *r, const sc *a, const sc *b) { sc t; sc_montmul(&t, a, b); sc_montmul(r, &t, &SC_RR); }
+/* Scalar::from_bytes_mod_order (src/cbor.rs:85) */
+static void sc_from_bytes_mod_order(sc *r, const u8 s[32]) {
+    sc a; for (int i = 0; i < 4; i++) a.v[i] = load64(s + 8 * i);
+    sc_montmul(r, &a, &SC_R);
+}
+/* Scalar::from_bytes_mod_order_wide (src/transcript.rs:153, Scalar::random) */
+static void sc_from_bytes_wide(sc *r, const u8 s[64]) {
+    sc lo, hi, a, b;
+    for (int i = 0; i < 4; i++) { lo.v[i] = load64(s + 8 * i); hi.v[i] = load64(s + 32 + 8 * i); }
+    sc_montmul(&a, &lo, &SC_R);
+    sc_montmul(&b, &hi, &SC_RR);
+    sc_add(r, &a, &b);
+}
+static void sc_tobytes(u8 s[32], const sc *a) { for (int i = 0; i < 4; i++) store64(s + 8 * i, a->v[i]); }
+static int sc_eq(const sc *a, const sc *b) { return memcmp(a->v, b->v, 32) == 0; }
+/* Scalar::invert: a^(l-2); 0 -> 0 */
+static void sc_invert(sc *r, const sc *a) {
+    u64 e[4] = {SC_L[0] - 2, SC_L[1], SC_L[2], SC_L[3]};
+    sc acc, base = *a;
+    sc_from_u64(&acc, 1);
+    for (int i = 0; i < 253; i++) {
+        if ((e[i / 64] >> (i % 64)) & 1) sc_mul(&acc, &acc, &base);
+        sc_mul(&base, &base, &base);
+    }
+    *r = acc;
+}
+static void sc_init(void) {
+    u64 inv = 1;
+    for (int i = 0; i < 6; i++) inv *= 2 - SC_L[0] * inv; /* l^{-1} mod 2^64 */
+    SC_LFACTOR = (u64)0 - inv;
+    u64 t[4] = {1, 0, 0, 0};
+    for (int i = 0; i < 512; i++) {
+        /* t = 2t mod l (t < l < 2^253) */
+        u64 c = 0;
+        for (int j = 0; j < 4; j++) { u64 n = (t[j] << 1) | c; c = t[j] >> 63; t[j] = n; }
+        if (sc_geq_l(t)) sc_sub_l(t);
+        if (i == 255) memcpy(SC_R.v, t, 32);
+    }
+    memcpy(SC_RR.v, t, 32);
+}
+/* dalek Scalar::as_radix_16: 64 signed digits in [-8,8) (top digit may reach 8) */
+static void sc_radix16(int8_t out[64], const sc *a) {
+    u8 b[32]; sc_tobytes(b, a);
+    for (int i = 0; i < 32; i++) { out[2 * i] = b[i] & 15; out[2 * i + 1] = (b[i] >> 4) & 15; }
+    for (int i = 0; i < 63; i++) {
+        int8_t carry = (int8_t)((out[i] + 8) >> 4);
+        out[i] = (int8_t)(out[i] - (carry << 4));
+        out[i + 1] = (int8_t)(out[i + 1] + carry);
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * twisted Edwards -x^2+y^2 = 1+dx^2y^2, extended coordinates; ristretto255 (RFC 9496)
+ * ---------------------------------------------------------------------------------- */
+typedef struct { fe X, Y, Z, T; } ge;           /* extended */
+typedef struct { fe YpX, YmX, Z, T2d; } ge_pn;  /* projective Niels */
+typedef struct { fe ypx, ymx, xy2d; } ge_an;    /* affine Niels */
+
+static ge GE_BASE; /* Ed25519/ristretto255 basepoint */
+
+static void ge_identity(ge *p) { fe_0(&p->X); fe_1(&p->Y); fe_1(&p->Z); fe_0(&p->T); }
+static void ge_to_pn(ge_pn *r, const ge *p) {
+    fe_add(&r->YpX, &p->Y, &p->X); fe_sub(&r->YmX, &p->Y, &p->X);
+    r->Z = p->Z; fe_mul(&r->T2d, &p->T, &FE_D2);
+}
+static void ge_pn_identity(ge_pn *r) { fe_1(&r->YpX); fe_1(&r->YmX); fe_1(&r->Z); fe_0(&r->T2d); }
+static void ge_an_identity(ge_an *r) { fe_1(&r->ypx); fe_1(&r->ymx); fe_0(&r->xy2d); }
+/* r = p + q (add-2008-hwcd-3 with a=-1, as dalek's EdwardsPoint + ProjectiveNiels) */
+static void ge_add_pn(ge *r, const ge *p, const ge_pn *q) {
+    fe YpX, YmX, PP, MM, TT2d, ZZ, ZZ2, E, F, G, H;
+    fe_add(&YpX, &p->Y, &p->X); fe_sub(&YmX, &p->Y, &p->X);
+    fe_mul(&PP, &YpX, &q->YpX); fe_mul(&MM, &YmX, &q->YmX);
+    fe_mul(&TT2d, &p->T, &q->T2d); fe_mul(&ZZ, &p->Z, &q->Z);
+    fe_add(&ZZ2, &ZZ, &ZZ);
+    fe_sub(&E, &PP, &MM); fe_add(&H, &PP, &MM); fe_add(&G, &ZZ2, &TT2d); fe_sub(&F, &ZZ2, &TT2d);
+    fe_mul(&r->X, &E, &F); fe_mul(&r->Y, &H, &G); fe_mul(&r->Z, &G, &F); fe_mul(&r->T, &E, &H);
+}
+static void ge_add_an(ge *r, const ge *p, const ge_an *q) {
+    fe YpX, YmX, PP, MM, Txy2d, Z2, E, F, G, H;
+    fe_add(&YpX, &p->Y, &p->X); fe_sub(&YmX, &p->Y, &p->X);
+    fe_mul(&PP, &YpX, &q->ypx); fe_mul(&MM, &YmX, &q->ymx);
+    fe_mul(&Txy2d, &p->T, &q->xy2d); fe_add(&Z2, &p->Z, &p->Z);
+    fe_sub(&E, &PP, &MM); fe_add(&H, &PP, &MM); fe_add(&G, &Z2, &Txy2d); fe_sub(&F, &Z2, &Txy2d);
+    fe_mul(&r->X, &E, &F); fe_mul(&r->Y, &H, &G); fe_mul(&r->Z, &G, &F); fe_mul(&r->T, &E, &H);
+}
+static void ge_add(ge *r, const ge *p, const ge *q) { ge_pn c; ge_to_pn(&c, q); ge_add_pn(r, p, &c); }
+static void ge_neg(ge *r, const ge *p) { fe_neg(&r->X, &p->X); r->Y = p->Y; r->Z = p->Z; fe_neg(&r->T, &p->T); }
+static void ge_sub(ge *r, const ge *p, const ge *q) { ge n; ge_neg(&n, q); ge_add(r, p, &n); }
+/* doubling (dalek ProjectivePoint::double); want_t=0 skips the T coordinate (4S+3M) */
+static void ge_dbl(ge *r, const ge *p, int want_t) {
+    fe XX, YY, ZZ2, XpY, XpY2, Yc, Zc, Xc, Tc;
+    fe_sq(&XX, &p->X); fe_sq(&YY, &p->Y); fe_sq(&ZZ2, &p->Z); fe_add(&ZZ2, &ZZ2, &ZZ2);
+    fe_add(&XpY, &p->X, &p->Y); fe_sq(&XpY2, &XpY);
+    fe_add(&Yc, &YY, &XX); fe_sub(&Zc, &YY, &XX); fe_sub(&Xc, &XpY2, &Yc); fe_sub(&Tc, &ZZ2, &Zc);
+    fe_mul(&r->X, &Xc, &Tc); fe_mul(&r->Y, &Yc, &Zc); fe_mul(&r->Z, &Zc, &Tc);
+    if (want_t) fe_mul(&r->T, &Xc, &Yc);
+}
+
+/* RFC 9496 4.3.1 Decode (dalek CompressedRistretto::decompress). returns 1 if valid */
+static int ristretto_decode(ge *p, const u8 bytes[32]) {
+    fe s, ss, u1, u2, u2_sqr, v, t, I, Dx, Dy, x, y;
+    u8 chk[32];
+    fe_frombytes(&s, bytes);
+    fe_tobytes(chk, &s);
+    if (memcmp(chk, bytes, 32) != 0) return 0;   /* non-canonical */
+    if (bytes[0] & 1) return 0;                  /* negative */
+    fe_sq(&ss, &s);
+    fe_sub(&u1, &FE_ONE, &ss); fe_add(&u2, &FE_ONE, &ss);
+    fe_sq(&u2_sqr, &u2);
+    fe_sq(&t, &u1); fe_mul(&t, &t, &FE_D); fe_neg(&t, &t); fe_sub(&v, &t, &u2_sqr);
+    fe_mul(&t, &v, &u2_sqr);
+    int ok = fe_sqrt_ratio_i(&I, &FE_ONE, &t);
+    fe_mul(&Dx, &I, &u2);
+    fe_mul(&Dy, &I, &Dx); fe_mul(&Dy, &Dy, &v);
+    fe_add(&x, &s, &s); fe_mul(&x, &x, &Dx);
+    fe_cneg(&x, fe_is_negative(&x));
+    fe_mul(&y, &u1, &Dy);
+    fe_mul(&t, &x, &y);
+    if (!ok || fe_is_negative(&t) || fe_is_zero(&y)) return 0;
+    p->X = x; p->Y = y; fe_1(&p->Z); p->T = t;
+    return 1;
+}
+/* RFC 9496 4.3.2 Encode (dalek RistrettoPoint::compress) */
+static void ristretto_encode(u8 out[32], const ge *p) {
+    fe u1, u2, t, I, i1, i2, z_inv, den_inv, iX, iY, ench, X, Y, s;
+    fe_add(&u1, &p->Z, &p->Y); fe_sub(&t, &p->Z, &p->Y); fe_mul(&u1, &u1, &t);
+    fe_mul(&u2, &p->X, &p->Y);
+    fe_sq(&t, &u2); fe_mul(&t, &t, &u1);
+    fe_sqrt_ratio_i(&I, &FE_ONE, &t);
+    fe_mul(&i1, &I, &u1); fe_mul(&i2, &I, &u2);
+    fe_mul(&t, &i2, &p->T); fe_mul(&z_inv, &i1, &t);
+    den_inv = i2;
+    fe_mul(&iX, &p->X, &FE_SQRT_M1); fe_mul(&iY, &p->Y, &FE_SQRT_M1);
+    fe_mul(&ench, &i1, &FE_INVSQRT_A_MINUS_D);
+    fe_mul(&t, &p->T, &z_inv);
+    int rotate = fe_is_negative(&t);
+    X = p->X; Y = p->Y;
+    fe_cmov(&X, &iY, rotate); fe_cmov(&Y, &iX, rotate); fe_cmov(&den_inv, &ench, rotate);
+    fe_mul(&t, &X, &z_inv);
+    fe_cneg(&Y, fe_is_negative(&t));
+    fe_sub(&t, &p->Z, &Y); fe_mul(&s, &den_inv, &t);
+    fe_cneg(&s, fe_is_negative(&s));
+    fe_tobytes(out, &s);
+}
+/* RFC 9496 4.3.4 MAP (dalek RistrettoPoint::elligator_ristretto_flavor) */
+static void ristretto_elligator(ge *p, const fe *r0) {
+    fe r, u, v, t, s, s_prime, c, N, w0, w1, w2, w3, ss, minus_one;
+    fe_neg(&minus_one, &FE_ONE);
+    fe_sq(&t, r0); fe_mul(&r, &FE_SQRT_M1, &t);
+    fe_add(&t, &r, &FE_ONE); fe_mul(&u, &t, &FE_ONE_MINUS_D_SQ);
+    fe_mul(&t, &r, &FE_D); fe_sub(&v, &minus_one, &t);
+    fe_add(&t, &r, &FE_D); fe_mul(&v, &v, &t);
+    int was_square = fe_sqrt_ratio_i(&s, &u, &v);
+    fe_mul(&s_prime, &s, r0);
+    fe_cneg(&s_prime, !fe_is_negative(&s_prime));
+    fe_cmov(&s, &s_prime, !was_square);
+    c = minus_one; fe_cmov(&c, &r, !was_square);
+    fe_sub(&t, &r, &FE_ONE); fe_mul(&N, &c, &t); fe_mul(&N, &N, &FE_D_MINUS_ONE_SQ); fe_sub(&N, &N, &v);
+    fe_sq(&ss, &s);
+    fe_add(&w0, &s, &s); fe_mul(&w0, &w0, &v);
+    fe_mul(&w1, &N, &FE_SQRT_AD_MINUS_ONE);
+    fe_sub(&w2, &FE_ONE, &ss); fe_add(&w3, &FE_ONE, &ss);
+    fe_mul(&p->X, &w0, &w3); fe_mul(&p->Y, &w2, &w1); fe_mul(&p->Z, &w1, &w3); fe_mul(&p->T, &w0, &w2);
+}
+/* RistrettoPoint::from_uniform_bytes (src/lib.rs:353) */
+static void ristretto_from_uniform(ge *p, const u8 b[64]) {
+    fe r1, r2; ge P1, P2;
+    fe_frombytes(&r1, b); fe_frombytes(&r2, b + 32);
+    ristretto_elligator(&P1, &r1); ristretto_elligator(&P2, &r2);
+    ge_add(p, &P1, &P2);
+}
+
+/* constant-time style selection from 8 multiples, signed digit in [-8,8] */
+static void pn_select(ge_pn *r, const ge_pn tab[8], int8_t d) {
+    int neg = d < 0; int abs = neg ? -d : d;
+    ge_pn_identity(r);
+    for (int j = 1; j <= 8; j++) {
+        int m = (abs == j);
+        fe_cmov(&r->YpX, &tab[j - 1].YpX, m); fe_cmov(&r->YmX, &tab[j - 1].YmX, m);
+        fe_cmov(&r->Z, &tab[j - 1].Z, m); fe_cmov(&r->T2d, &tab[j - 1].T2d, m);
+    }
+    fe a = r->YpX, b = r->YmX;
+    fe_cmov(&r->YpX, &b, neg); fe_cmov(&r->YmX, &a, neg); fe_cneg(&r->T2d, neg);
+}
+static void an_select(ge_an *r, const ge_an tab[8], int8_t d) {
+    int neg = d < 0; int abs = neg ? -d : d;
+    ge_an_identity(r);
+    for (int j = 1; j <= 8; j++) {
+        int m = (abs == j);
+        fe_cmov(&r->ypx, &tab[j - 1].ypx, m); fe_cmov(&r->ymx, &tab[j - 1].ymx, m);
+        fe_cmov(&r->xy2d, &tab[j - 1].xy2d, m);
+    }
+    fe a = r->ypx, b = r->ymx;
+    fe_cmov(&r->ypx, &b, neg); fe_cmov(&r->ymx, &a, neg); fe_cneg(&r->xy2d, neg);
+}
+/* dalek backend::serial::scalar_mul::variable_base::mul -- `RistrettoPoint * Scalar`.
+ * Radix-16 signed digits, 8-entry table, 63 x (4 doublings + 1 addition). */
+static void ge_scalarmult(ge *r, const ge *p, const sc *s) {
+    ge_pn tab[8], sel; ge q, t;
+    int8_t dig[64];
+    ge_to_pn(&tab[0], p);
+    q = *p;
+    for (int j = 1; j < 8; j++) { ge_add_pn(&t, p, &tab[j - 1]); ge_to_pn(&tab[j], &t); }
+    sc_radix16(dig, s);
+    ge_identity(&q);
+    pn_select(&sel, tab, dig[63]);
+    ge_add_pn(&q, &q, &sel);
+    for (int i = 62; i >= 0; i--) {
+        ge_dbl(&q, &q, 0); ge_dbl(&q, &q, 0); ge_dbl(&q, &q, 0); ge_dbl(&q, &q, 1);
+        pn_select(&sel, tab, dig[i]);
+        ge_add_pn(&q, &q, &sel);
+    }
+    *r = q;
+}
+/* dalek RistrettoBasepointTable (EdwardsBasepointTableRadix16): 32 tables of 8 affine-Niels
+ * multiples of 256^i B */
+typedef struct { ge_an t[32][8]; ge base; } ge_table;
+static void ge_to_an(ge_an *r, const ge *p) {
+    fe zi, x, y, xy;
+    fe_invert(&zi, &p->Z); fe_mul(&x, &p->X, &zi); fe_mul(&y, &p->Y, &zi);
+    fe_add(&r->ypx, &y, &x); fe_sub(&r->ymx, &y, &x);
+    fe_mul(&xy, &x, &y); fe_mul(&r->xy2d, &xy, &FE_D2);
+}
+static void ge_table_create(ge_table *T, const ge *b) {
+    ge P = *b;
+    T->base = *b;
+    for (int i = 0; i < 32; i++) {
+        ge Q = P;
+        for (int j = 0; j < 8; j++) {
+            ge_to_an(&T->t[i][j], &Q);
+            ge_add(&Q, &Q, &P);
+        }
+        for (int k = 0; k < 8; k++) ge_dbl(&P, &P, 1); /* P = 256 P */
+    }
+}
+/* dalek EdwardsBasepointTable::mul_base: `&table * &scalar` */
+static void ge_table_mul(ge *r, const ge_table *T, const sc *s) {
+    int8_t a[64]; ge_an sel; ge P;
+    sc_radix16(a, s);
+    ge_identity(&P);
+    for (int i = 1; i < 64; i += 2) { an_select(&sel, T->t[i / 2], a[i]); ge_add_an(&P, &P, &sel); }
+    ge_dbl(&P, &P, 0); ge_dbl(&P, &P, 0); ge_dbl(&P, &P, 0); ge_dbl(&P, &P, 1);
+    for (int i = 0; i < 64; i += 2) { an_select(&sel, T->t[i / 2], a[i]); ge_add_an(&P, &P, &sel); }
+    *r = P;
+}
+
+/* ------------------------------------------------------------------------------------
+ * BLAKE3 (hash mode, arbitrary-length output) -- one-shot, recursive over the chunk tree
+ * ---------------------------------------------------------------------------------- */
+static const u32 B3_IV[8] = {0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A,
+                             0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19};
+static const u8 B3_PERM[16] = {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8};
+enum { B3_CHUNK_START = 1, B3_CHUNK_END = 2, B3_PARENT = 4, B3_ROOT = 8 };
+static u32 rotr32(u32 x, int n) { return (x >> n) | (x << (32 - n)); }
+#define B3_G(a, b, c, d, x, y)                                                  \
+    do {                                                                        \
+        st[a] = st[a] + st[b] + (x); st[d] = rotr32(st[d] ^ st[a], 16);         \
+        st[c] = st[c] + st[d];       st[b] = rotr32(st[b] ^ st[c], 12);         \
+        st[a] = st[a] + st[b] + (y); st[d] = rotr32(st[d] ^ st[a], 8);          \
+        st[c] = st[c] + st[d];       st[b] = rotr32(st[b] ^ st[c], 7);          \
+    } while (0)
+static void b3_compress(const u32 cv[8], const u32 block[16], u64 counter, u32 blen, u32 flags, u32 out[16]) {
+    u32 st[16], m[16], t[16];
+    memcpy(m, block, 64);
+    for (int i = 0; i < 8; i++) st[i] = cv[i];
+    st[8] = B3_IV[0]; st[9] = B3_IV[1]; st[10] = B3_IV[2]; st[11] = B3_IV[3];
+    st[12] = (u32)counter; st[13] = (u32)(counter >> 32); st[14] = blen; st[15] = flags;
+    for (int r = 0; r < 7; r++) {
+        B3_G(0, 4, 8, 12, m[0], m[1]);  B3_G(1, 5, 9, 13, m[2], m[3]);
+        B3_G(2, 6, 10, 14, m[4], m[5]); B3_G(3, 7, 11, 15, m[6], m[7]);
+        B3_G(0, 5, 10, 15, m[8], m[9]); B3_G(1, 6, 11, 12, m[10], m[11]);
+        B3_G(2, 7, 8, 13, m[12], m[13]); B3_G(3, 4, 9, 14, m[14], m[15]);
+        for (int i = 0; i < 16; i++) t[i] = m[B3_PERM[i]];
+        memcpy(m, t, 64);
+    }
+    for (int i = 0; i < 8; i++) { out[i] = st[i] ^ st[i + 8]; out[i + 8] = st[i + 8] ^ cv[i]; }
+}
+static void b3_words(u32 w[16], const u8 *p, size_t n) {
+    u8 buf[64]; memset(buf, 0, 64); memcpy(buf, p, n);
+    for (int i = 0; i < 16; i++) w[i] = (u32)buf[4 * i] | (u32)buf[4 * i + 1] << 8 | (u32)buf[4 * i + 2] << 16 | (u32)buf[4 * i + 3] << 24;
+}
+/* A node ready for its final compression: either the last block of a chunk or a parent. */
+typedef struct { u32 cv[8]; u32 block[16]; u64 counter; u32 blen; u32 flags; } b3_node;
+static void b3_chunk_node(b3_node *nd, const u8 *p, size_t n, u64 chunk_counter) {
+    u32 cv[8], w[16], out[16];
+    memcpy(cv, B3_IV, 32);
+    u32 flags = B3_CHUNK_START;
+    while (n > 64) {
+        b3_words(w, p, 64);
+        b3_compress(cv, w, chunk_counter, 64, flags, out);
+        memcpy(cv, out, 32);
+        flags = 0; p += 64; n -= 64;
+    }
+    memcpy(nd->cv, cv, 32);
+    b3_words(nd->block, p, n);
+    nd->counter = chunk_counter; nd->blen = (u32)n; nd->flags = flags | B3_CHUNK_END;
+}
+static void b3_subtree(b3_node *nd, const u8 *p, size_t n, u64 chunk_counter) {
+    if (n <= 1024) { b3_chunk_node(nd, p, n, chunk_counter); return; }
+    /* left subtree: largest power-of-two number of chunks that leaves >= 1 byte on the right */
+    size_t chunks = (n - 1) / 1024, left = 1;
+    while (left * 2 <= chunks) left *= 2;
+    b3_node l, r; u32 out[16];
+    b3_subtree(&l, p, left * 1024, chunk_counter);
+    b3_subtree(&r, p + left * 1024, n - left * 1024, chunk_counter + left);
+    memcpy(nd->cv, B3_IV, 32);
+    b3_compress(l.cv, l.block, l.counter, l.blen, l.flags, out); memcpy(nd->block, out, 32);
+    b3_compress(r.cv, r.block, r.counter, r.blen, r.flags, out); memcpy(nd->block + 8, out, 32);
+    nd->counter = 0; nd->blen = 64; nd->flags = B3_PARENT;
+}
+static void blake3_xof(const u8 *in, size_t n, u8 *out, size_t outlen) {
+    b3_node root; u32 o[16]; u64 ctr = 0;
+    b3_subtree(&root, in, n, 0);
+    while (outlen) {
+        b3_compress(root.cv, root.block, ctr++, root.blen, root.flags | B3_ROOT, o);
+        for (int i = 0; i < 64 && outlen; i++, outlen--) *out++ = (u8)(o[i / 4] >> (8 * (i % 4)));
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * Params (src/lib.rs:222-229,291-354) and Transcript (src/transcript.rs:29-155)
+ * ---------------------------------------------------------------------------------- */
+typedef struct { ge_table h1, h2, h3; } act_params;
+
+static void store_u64be(u8 *p, u64 x) { for (int i = 7; i >= 0; i--) { p[i] = (u8)x; x >>= 8; } }
+
+static const char PROTOCOL_VERSION[] = "curve25519-ristretto anonymous-credits v1.0"; /* transcript.rs:29 */
+
+#define TR_MAX (184 + 8 + 40 * 400)
+typedef struct { u8 buf[TR_MAX]; size_t len; } transcript;
+static void tr_raw(transcript *t, const void *p, size_t n) { memcpy(t->buf + t->len, p, n); t->len += n; }
+static void tr_update(transcript *t, const u8 *p, size_t n) { /* transcript.rs:95-98 */
+    u8 l[8]; store_u64be(l, n); tr_raw(t, l, 8); tr_raw(t, p, n);
+}
+static void tr_add_element(transcript *t, const ge *p) { u8 e[32]; ristretto_encode(e, p); tr_update(t, e, 32); }
+static void tr_add_scalar(transcript *t, const sc *s) { u8 e[32]; sc_tobytes(e, s); tr_update(t, e, 32); }
+static void tr_new(transcript *t, const act_params *P, const char *label) { /* transcript.rs:54-74 */
+    u8 l[8];
+    t->len = 0;
+    store_u64be(l, strlen(PROTOCOL_VERSION)); tr_raw(t, l, 8); tr_raw(t, PROTOCOL_VERSION, strlen(PROTOCOL_VERSION));
+    tr_add_element(t, &P->h1.base); tr_add_element(t, &P->h2.base); tr_add_element(t, &P->h3.base);
+    store_u64be(l, strlen(label)); tr_raw(t, l, 8); tr_raw(t, label, strlen(label));
+}
+static void tr_challenge(sc *out, const transcript *t) { /* transcript.rs:149-154 */
+    u8 o[64]; blake3_xof(t->buf, t->len, o, 64); sc_from_bytes_wide(out, o);
+}
+
+static void hash_to_ristretto(ge *p, const char *dom, const u8 seed[32], u32 counter) { /* lib.rs:332-354 */
+    u8 buf[512 + 64]; size_t n = 0, dl = strlen(dom);
+    store_u64be(buf + n, dl); n += 8; memcpy(buf + n, dom, dl); n += dl;
+    store_u64be(buf + n, 32); n += 8; memcpy(buf + n, seed, 32); n += 32;
+    store_u64be(buf + n, 4); n += 8;
+    buf[n++] = (u8)counter; buf[n++] = (u8)(counter >> 8); buf[n++] = (u8)(counter >> 16); buf[n++] = (u8)(counter >> 24);
+    u8 uni[64]; blake3_xof(buf, n, uni, 64);
+    ristretto_from_uniform(p, uni);
+}
+static int params_points_new(ge h[3], const char *org, const char *svc, const char *dep, const char *ver) { /* lib.rs:291-315 */
+    char dom[400]; u8 buf[512]; u8 seed[32];
+    if (strlen(org) + strlen(svc) + strlen(dep) + strlen(ver) > 380) return -1;
+    strcpy(dom, "ACT-v1:"); strcat(dom, org); strcat(dom, ":"); strcat(dom, svc); strcat(dom, ":");
+    strcat(dom, dep); strcat(dom, ":"); strcat(dom, ver);
+    size_t dl = strlen(dom);
+    store_u64be(buf, dl); memcpy(buf + 8, dom, dl);
+    blake3_xof(buf, 8 + dl, seed, 32);
+    for (u32 i = 0; i < 3; i++) hash_to_ristretto(&h[i], dom, seed, i);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * one-time init + self test of constants
+ * ---------------------------------------------------------------------------------- */
+static int g_init_done = 0;
+static ge_table GE_BASE_TABLE;
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+static void oracle_init_impl(void) {
+    fe_1(&FE_ONE);
+    fe_fromhex(&FE_D, "a3785913ca4deb75abd841414d0a700098e879777940c78c73fe6f2bee6c0352");
+    fe_fromhex(&FE_D2, "59f1b226949bd6eb56b183829a14e00030d1f3eef2808e19e7fcdf56dcd90624");
+    fe_fromhex(&FE_SQRT_M1, "b0a00e4a271beec478e42fad0618432fa7d7fb3d99004d2b0bdfc14f8024832b");
+    fe_fromhex(&FE_SQRT_AD_MINUS_ONE, "1b2e7b49a0f6977ebd54781b0c8e9daffdd1f531c9fc3c0fac48832bbf316937");
+    fe_fromhex(&FE_INVSQRT_A_MINUS_D, "ea405d80aafdc899be72415a17162f9d40d801fe917bc216a2fcafcf05896c78");
+    fe_fromhex(&FE_ONE_MINUS_D_SQ, "76c15f94c1097ce20f355ecd38a1812ce4df70beddab9499d7e0b3b2a8729002");
+    fe_fromhex(&FE_D_MINUS_ONE_SQ, "204ded44aa5aad3199191eb02c4a9ed2eb4e9b522fd3dc4c41226cf67ab36859");
+    sc_init();
+    /* basepoint: y = 4/5, x even */
+    fe four, five, y, yy, u, v, x;
+    fe_0(&four); four.v[0] = 4; fe_0(&five); five.v[0] = 5;
+    fe_invert(&five, &five); fe_mul(&y, &four, &five);
+    fe_sq(&yy, &y); fe_sub(&u, &yy, &FE_ONE); fe_mul(&v, &yy, &FE_D); fe_add(&v, &v, &FE_ONE);
+    fe_sqrt_ratio_i(&x, &u, &v); /* returns the non-negative (even) root */
+    GE_BASE.X = x; GE_BASE.Y = y; fe_1(&GE_BASE.Z); fe_mul(&GE_BASE.T, &x, &y);
+    ge_table_create(&GE_BASE_TABLE, &GE_BASE);
+    g_init_done = 1;
+}
+static void oracle_init(void) { pthread_once(&g_once, oracle_init_impl); }
+
+/* ------------------------------------------------------------------------------------
+ * Protocol (typed)
+ * ---------------------------------------------------------------------------------- */
+enum {
+    ST_OK = 0,
+    ST_INVALID_ISSUANCE_REQUEST_PROOF = 1, /* Error discriminant + 1, src/lib.rs:102-112 */
+    ST_INVALID_ISSUANCE_RESPONSE_PROOF = 2,
+    ST_DOUBLE_SPEND = 3,
+    ST_INVALID_REFUND_PROOF = 4,
+    ST_INVALID_REFUND_RESPONSE_PROOF = 5,
+    ST_IDENTITY_POINT = 6,
+    ST_INVALID_CLIENT_SPEND_PROOF = 7,
+    ST_AMOUNT_TOO_BIG = 8,
+    ST_SCALAR_OUT_OF_RANGE = 9,
+    ST_DECODE_INVALID_POINT = 0x81, /* CborError::InvalidValue("invalid Ristretto point"), src/cbor.rs:71 */
+    ST_DECODE_BAD_STRUCTURE = 0x82,
+    ST_DECODE_PARSER = 0x83
+};
+
+typedef struct { sc x; ge w; } act_key;
+
+static void scalar_random(sc *s, const u8 **rnd) { sc_from_bytes_wide(s, *rnd); *rnd += 64; } /* Scalar::random */
+
+/* PrivateKey::issue, src/lib.rs:621-663.  Typed inputs; rnd = 128 bytes (e then alpha), used only on accept. */
+typedef struct { ge K; sc gamma, k_bar, r_bar; } issuance_request;
+typedef struct { ge A; sc e, gamma, z, c; } issuance_response;
+static int act_issue(const act_params *P, const act_key *key, const issuance_request *rq, const sc *c,
+                     const u8 *rnd, issuance_response *out) {
+    ge t1, t2, k1; sc gamma;
+    transcript tr;
+    ge_table_mul(&t1, &P->h2, &rq->k_bar); ge_table_mul(&t2, &P->h3, &rq->r_bar); ge_add(&t1, &t1, &t2);
+    ge_scalarmult(&t2, &rq->K, &rq->gamma); ge_sub(&k1, &t1, &t2);                    /* :629-630 */
+    tr_new(&tr, P, "request"); tr_add_element(&tr, &rq->K); tr_add_element(&tr, &k1);   /* :633-635 */
+    tr_challenge(&gamma, &tr);
+    if (!sc_eq(&gamma, &rq->gamma)) return ST_INVALID_ISSUANCE_REQUEST_PROOF;           /* :638-640 */
+    sc e, alpha, ex, inv;
+    ge x_a, a, x_g, y_a, y_g;
+    scalar_random(&e, &rnd);                                                            /* :643 */
+    ge_table_mul(&t1, &P->h1, c); ge_add(&x_a, &GE_BASE, &t1); ge_add(&x_a, &x_a, &rq->K); /* :644 */
+    sc_add(&ex, &e, &key->x); sc_invert(&inv, &ex); ge_scalarmult(&a, &x_a, &inv);      /* :645 */
+    ge_scalarmult(&t1, &GE_BASE, &e); ge_add(&x_g, &t1, &key->w);                       /* :646 */
+    scalar_random(&alpha, &rnd);                                                        /* :649 */
+    ge_scalarmult(&y_a, &a, &alpha); ge_scalarmult(&y_g, &GE_BASE, &alpha);             /* :650-651 */
+    tr_new(&tr, P, "respond");                                                          /* :654-657 */
+    tr_add_scalar(&tr, c); tr_add_scalar(&tr, &e);
+    tr_add_element(&tr, &a); tr_add_element(&tr, &x_a); tr_add_element(&tr, &x_g);
+    tr_add_element(&tr, &y_a); tr_add_element(&tr, &y_g);
+    tr_challenge(&gamma, &tr);
+    sc z; sc_mul(&z, &gamma, &ex); sc_add(&z, &z, &alpha);                              /* :660 */
+    out->A = a; out->e = e; out->gamma = gamma; out->z = z; out->c = *c;
+    return ST_OK;
+}
+
+/* PreIssuance::request, src/lib.rs:463-487 (fixtures). rnd = 128 bytes (k', r') */
+static void act_request(const act_params *P, const sc *r, const sc *k, const u8 *rnd, issuance_request *out) {
+    ge t1, t2, big_k, k1; sc k_prime, r_prime, gamma, t; transcript tr;
+    ge_table_mul(&t1, &P->h2, k); ge_table_mul(&t2, &P->h3, r); ge_add(&big_k, &t1, &t2);
+    scalar_random(&k_prime, &rnd); scalar_random(&r_prime, &rnd);
+    ge_table_mul(&t1, &P->h2, &k_prime); ge_table_mul(&t2, &P->h3, &r_prime); ge_add(&k1, &t1, &t2);
+    tr_new(&tr, P, "request"); tr_add_element(&tr, &big_k); tr_add_element(&tr, &k1);
+    tr_challenge(&gamma, &tr);
+    out->K = big_k; out->gamma = gamma;
+    sc_mul(&t, k, &gamma); sc_add(&out->k_bar, &k_prime, &t);
+    sc_mul(&t, r, &gamma); sc_add(&out->r_bar, &r_prime, &t);
+}
+
+/* verification half of PreIssuance::to_credit_token, src/lib.rs:528-562 */
+static int act_issuance_check(const act_params *P, const ge *w, const ge *K, const issuance_response *rs) {
+    ge t1, t2, x_a, x_g, y_a, y_g; sc ng, gamma; transcript tr;
+    ge_table_mul(&t1, &P->h1, &rs->c); ge_add(&x_a, &GE_BASE, &t1); ge_add(&x_a, &x_a, K);   /* :536 */
+    ge_scalarmult(&t1, &GE_BASE, &rs->e); ge_add(&x_g, &t1, w);                              /* :537 */
+    sc_neg(&ng, &rs->gamma);
+    ge_scalarmult(&t1, &rs->A, &rs->z); ge_scalarmult(&t2, &x_a, &ng); ge_add(&y_a, &t1, &t2);    /* :540 */
+    ge_scalarmult(&t1, &GE_BASE, &rs->z); ge_scalarmult(&t2, &x_g, &ng); ge_add(&y_g, &t1, &t2);  /* :541 */
+    tr_new(&tr, P, "respond");                                                               /* :544-547 */
+    tr_add_scalar(&tr, &rs->c); tr_add_scalar(&tr, &rs->e);
+    tr_add_element(&tr, &rs->A); tr_add_element(&tr, &x_a); tr_add_element(&tr, &x_g);
+    tr_add_element(&tr, &y_a); tr_add_element(&tr, &y_g);
+    tr_challenge(&gamma, &tr);
+    return sc_eq(&gamma, &rs->gamma) ? ST_OK : ST_INVALID_ISSUANCE_RESPONSE_PROOF;           /* :550-552 */
+}
+
+typedef struct {
+    sc k, s; ge a_prime, b_bar; ge com[ACT_L];
+    sc gamma, e_bar, r2_bar, r3_bar, c_bar, r_bar, w00, w01;
+    sc gamma0[ACT_L]; sc z[ACT_L][2]; sc k_bar, s_bar;
+} spend_proof; /* src/lib.rs:673-708 */
+typedef struct { ge A; sc e, gamma, z; } refund_t; /* src/lib.rs:1161-1170 */
+
+static void sc_pow2(sc *r, int i) { sc_zero(r); r->v[i / 64] = 1ULL << (i % 64); } /* Scalar::from(2u128.pow(i)) */
+
+static int ge_is_identity_ristretto(const ge *p) { /* RistrettoPoint == identity: X1*Y2==Y1*X2 | X1*X2==Y1*Y2 */
+    return fe_is_zero(&p->X) || fe_is_zero(&p->Y);
+}
+
+/* PrivateKey::refund, src/lib.rs:781-869.  rnd = 128 bytes (e then alpha), used only on accept. */
+static int act_refund(const act_params *P, const act_key *key, const spend_proof *sp, const u8 *rnd, refund_t *out) {
+    ge t1, t2, t3;
+    if (ge_is_identity_ristretto(&sp->a_prime)) return ST_IDENTITY_POINT;                /* :787-789 */
+    ge a_bar, big_h1, a1, a2;
+    sc ngamma; sc_neg(&ngamma, &sp->gamma);
+    ge_scalarmult(&a_bar, &sp->a_prime, &key->x);                                        /* :791 */
+    ge_table_mul(&t1, &P->h2, &sp->k); ge_add(&big_h1, &GE_BASE, &t1);                   /* :792 */
+    ge_scalarmult(&t1, &sp->a_prime, &sp->e_bar); ge_scalarmult(&t2, &sp->b_bar, &sp->r2_bar);
+    ge_scalarmult(&t3, &a_bar, &ngamma);
+    ge_add(&a1, &t1, &t2); ge_add(&a1, &a1, &t3);                                        /* :793-795 */
+    ge_scalarmult(&t1, &sp->b_bar, &sp->r3_bar); ge_table_mul(&t2, &P->h1, &sp->c_bar);
+    ge_add(&a2, &t1, &t2);
+    ge_table_mul(&t1, &P->h3, &sp->r_bar); ge_add(&a2, &a2, &t1);
+    ge_scalarmult(&t1, &big_h1, &ngamma); ge_add(&a2, &a2, &t1);                         /* :796-799 */
+    static __thread ge cprime[ACT_L][2];
+    for (int j = 0; j < ACT_L; j++) {                                                    /* :800-817 */
+        sc g01; ge c1;
+        sc_sub(&g01, &sp->gamma, &sp->gamma0[j]);
+        ge_sub(&c1, &sp->com[j], &P->h1.base);
+        if (j == 0) {
+            ge_table_mul(&t1, &P->h2, &sp->w00); ge_table_mul(&t2, &P->h3, &sp->z[0][0]); ge_add(&t1, &t1, &t2);
+            ge_scalarmult(&t2, &sp->com[0], &sp->gamma0[0]); ge_sub(&cprime[0][0], &t1, &t2);
+            ge_table_mul(&t1, &P->h2, &sp->w01); ge_table_mul(&t2, &P->h3, &sp->z[0][1]); ge_add(&t1, &t1, &t2);
+            ge_scalarmult(&t2, &c1, &g01); ge_sub(&cprime[0][1], &t1, &t2);
+        } else {
+            ge_table_mul(&t1, &P->h3, &sp->z[j][0]); ge_scalarmult(&t2, &sp->com[j], &sp->gamma0[j]);
+            ge_sub(&cprime[j][0], &t1, &t2);
+            ge_table_mul(&t1, &P->h3, &sp->z[j][1]); ge_scalarmult(&t2, &c1, &g01);
+            ge_sub(&cprime[j][1], &t1, &t2);
+        }
+    }
+    ge k_prime; ge_identity(&k_prime);                                                   /* :819-824 */
+    for (int i = 0; i < ACT_L; i++) { sc p2; sc_pow2(&p2, i); ge_scalarmult(&t1, &sp->com[i], &p2); ge_add(&k_prime, &k_prime, &t1); }
+    ge com_, big_c; sc nc;
+    ge_table_mul(&t1, &P->h1, &sp->s); ge_add(&com_, &t1, &k_prime);                     /* :825 */
+    sc_neg(&nc, &sp->c_bar);
+    ge_table_mul(&t1, &P->h1, &nc); ge_table_mul(&t2, &P->h2, &sp->k_bar); ge_add(&big_c, &t1, &t2);
+    ge_table_mul(&t1, &P->h3, &sp->s_bar); ge_add(&big_c, &big_c, &t1);
+    ge_scalarmult(&t1, &com_, &sp->gamma); ge_sub(&big_c, &big_c, &t1);                  /* :826-829 */
+    static __thread transcript tr;
+    sc gamma;
+    tr_new(&tr, P, "spend");                                                             /* :831-840 */
+    tr_add_scalar(&tr, &sp->k);
+    tr_add_element(&tr, &sp->a_prime); tr_add_element(&tr, &sp->b_bar);
+    tr_add_element(&tr, &a1); tr_add_element(&tr, &a2);
+    for (int j = 0; j < ACT_L; j++) tr_add_element(&tr, &sp->com[j]);
+    for (int j = 0; j < ACT_L; j++) { tr_add_element(&tr, &cprime[j][0]); tr_add_element(&tr, &cprime[j][1]); }
+    tr_add_element(&tr, &big_c);
+    tr_challenge(&gamma, &tr);
+    if (!sc_eq(&gamma, &sp->gamma)) return ST_INVALID_CLIENT_SPEND_PROOF;                /* :842-844 */
+    sc e, alpha, ex, inv, z;
+    ge x_a, a, x_g, y_a, y_g;
+    scalar_random(&e, &rnd);                                                             /* :846 */
+    ge_add(&x_a, &GE_BASE, &k_prime);                                                    /* :848 */
+    sc_add(&ex, &e, &key->x); sc_invert(&inv, &ex); ge_scalarmult(&a, &x_a, &inv);       /* :849 */
+    ge_scalarmult(&t1, &GE_BASE, &e); ge_add(&x_g, &t1, &key->w);                        /* :851 */
+    scalar_random(&alpha, &rnd);                                                         /* :852 */
+    ge_scalarmult(&y_a, &a, &alpha); ge_scalarmult(&y_g, &GE_BASE, &alpha);              /* :853-854 */
+    tr_new(&tr, P, "refund");                                                            /* :856-859 */
+    tr_add_scalar(&tr, &e);
+    tr_add_element(&tr, &a); tr_add_element(&tr, &x_a); tr_add_element(&tr, &x_g);
+    tr_add_element(&tr, &y_a); tr_add_element(&tr, &y_g);
+    tr_challenge(&gamma, &tr);
+    sc_mul(&z, &gamma, &ex); sc_add(&z, &z, &alpha);                                     /* :861 */
+    out->A = a; out->e = e; out->gamma = gamma; out->z = z;
+    return ST_OK;
+}
+
+/* verification half of PreRefund::to_credit_token, src/lib.rs:1217-1253 */
+static int act_refund_check(const act_params *P, const ge *w, const ge com[ACT_L], const refund_t *rf) {
+    ge t1, t2, x_a, x_g, y_a, y_g; sc ng, gamma; transcript tr;
+    ge_identity(&t2);
+    for (int i = 0; i < ACT_L; i++) { sc p2; sc_pow2(&p2, i); ge_scalarmult(&t1, &com[i], &p2); ge_add(&t2, &t2, &t1); }
+    ge_add(&x_a, &GE_BASE, &t2);                                                          /* :1224-1230 */
+    ge_scalarmult(&t1, &GE_BASE, &rf->e); ge_add(&x_g, &t1, w);                           /* :1232 */
+    sc_neg(&ng, &rf->gamma);
+    ge_scalarmult(&t1, &rf->A, &rf->z); ge_scalarmult(&t2, &x_a, &ng); ge_add(&y_a, &t1, &t2);    /* :1233 */
+    ge_scalarmult(&t1, &GE_BASE, &rf->z); ge_scalarmult(&t2, &x_g, &ng); ge_add(&y_g, &t1, &t2);  /* :1234 */
+    tr_new(&tr, P, "refund");                                                             /* :1236-1239 */
+    tr_add_scalar(&tr, &rf->e);
+    tr_add_element(&tr, &rf->A); tr_add_element(&tr, &x_a); tr_add_element(&tr, &x_g);
+    tr_add_element(&tr, &y_a); tr_add_element(&tr, &y_g);
+    tr_challenge(&gamma, &tr);
+    return sc_eq(&gamma, &rf->gamma) ? ST_OK : ST_INVALID_REFUND_PROOF;                   /* :1241-1243 */
+}
+
+/* CreditToken::prove_spend, src/lib.rs:972-1152 (fixtures).  rnd = 524*64 bytes in the order of
+ * SURVEY Appendix B.  token = (a,e,k,r,c).  Outputs proof and PreRefund (k*, r*, m). */
+typedef struct { ge a; sc e, k, r, c; } credit_token;
+static void sc_csel(sc *r, const sc *a, const sc *b, int choice) { *r = choice ? *b : *a; } /* conditional_select(a,b,choice) */
+static void act_prove_spend(const act_params *P, const credit_token *tk, const sc *s, const u8 *rnd,
+                            spend_proof *sp, sc *pr_k, sc *pr_r, sc *pr_m) {
+    sc r1, r2, c_prime, r_prime, e_prime, r2_prime, r3_prime, r3, t, m;
+    ge t1, t2, b, a_prime, b_bar, a1, a2;
+    scalar_random(&r1, &rnd); scalar_random(&r2, &rnd); scalar_random(&c_prime, &rnd);
+    scalar_random(&r_prime, &rnd); scalar_random(&e_prime, &rnd); scalar_random(&r2_prime, &rnd);
+    scalar_random(&r3_prime, &rnd);                                                      /* :978-984 */
+    ge_table_mul(&t1, &P->h1, &tk->c); ge_add(&b, &GE_BASE, &t1);
+    ge_table_mul(&t1, &P->h2, &tk->k); ge_add(&b, &b, &t1);
+    ge_table_mul(&t1, &P->h3, &tk->r); ge_add(&b, &b, &t1);                              /* :986-989 */
+    sc_mul(&t, &r1, &r2); ge_scalarmult(&a_prime, &tk->a, &t);                           /* :990 */
+    ge_scalarmult(&b_bar, &b, &r1);                                                      /* :991 */
+    sc_invert(&r3, &r1);                                                                 /* :992 */
+    ge_scalarmult(&t1, &a_prime, &e_prime); ge_scalarmult(&t2, &b_bar, &r2_prime); ge_add(&a1, &t1, &t2); /* :993 */
+    ge_scalarmult(&t1, &b_bar, &r3_prime); ge_table_mul(&t2, &P->h1, &c_prime); ge_add(&a2, &t1, &t2);
+    ge_table_mul(&t1, &P->h3, &r_prime); ge_add(&a2, &a2, &t1);                          /* :994 */
+    sc_sub(&m, &tk->c, s);
+    int bit[ACT_L]; u8 mb[32]; sc_tobytes(mb, &m);
+    for (int i = 0; i < ACT_L; i++) bit[i] = (mb[i / 8] >> (i % 8)) & 1;                 /* bits_of :902-915 */
+    sc k_star; static __thread sc s_i[ACT_L], s_i_prime[ACT_L], gamma_i[ACT_L], zr[ACT_L];
+    scalar_random(&k_star, &rnd);                                                        /* :998 */
+    for (int j = 0; j < ACT_L; j++) scalar_random(&s_i[j], &rnd);                        /* :999 */
+    for (int j = 0; j < ACT_L; j++) {                                                    /* :1000-1004 */
+        sc ij; sc_from_u64(&ij, (u64)bit[j]);
+        ge_table_mul(&t1, &P->h1, &ij);
+        if (j == 0) { ge_table_mul(&t2, &P->h2, &k_star); ge_add(&t1, &t1, &t2); }
+        ge_table_mul(&t2, &P->h3, &s_i[j]); ge_add(&sp->com[j], &t1, &t2);
+    }
+    sc k0_prime, w0;
+    scalar_random(&k0_prime, &rnd);                                                      /* :1010 */
+    for (int j = 0; j < ACT_L; j++) scalar_random(&s_i_prime[j], &rnd);                  /* :1011-1014 */
+    for (int j = 0; j < ACT_L; j++) scalar_random(&gamma_i[j], &rnd);                    /* :1015-1018 */
+    scalar_random(&w0, &rnd);                                                            /* :1019 */
+    for (int j = 0; j < ACT_L; j++) scalar_random(&zr[j], &rnd);                         /* :1020-1023 */
+    static __thread ge cprime[ACT_L][2];
+    for (int j = 0; j < ACT_L; j++) {                                                    /* :1025-1051 */
+        ge c0 = sp->com[j], c1, sim0, sim1, real;
+        ge_sub(&c1, &sp->com[j], &P->h1.base);
+        /* simulated branch for each side, and the real commitment */
+        if (j == 0) {
+            ge_table_mul(&t1, &P->h2, &w0); ge_table_mul(&t2, &P->h3, &zr[0]); ge_add(&t1, &t1, &t2);
+            ge_scalarmult(&t2, &c0, &gamma_i[0]); ge_sub(&sim0, &t1, &t2);
+            ge_scalarmult(&t2, &c1, &gamma_i[0]); ge_sub(&sim1, &t1, &t2);
+            ge_table_mul(&t1, &P->h2, &k0_prime); ge_table_mul(&t2, &P->h3, &s_i_prime[0]); ge_add(&real, &t1, &t2);
+        } else {
+            ge_table_mul(&t1, &P->h3, &zr[j]);
+            ge_scalarmult(&t2, &c0, &gamma_i[j]); ge_sub(&sim0, &t1, &t2);
+            ge_scalarmult(&t2, &c1, &gamma_i[j]); ge_sub(&sim1, &t1, &t2);
+            ge_table_mul(&real, &P->h3, &s_i_prime[j]);
+        }
+        int is0 = (bit[j] == 0);
+        /* conditional_select(a, b, choice) = choice ? b : a */
+        cprime[j][0] = is0 ? real : sim0;
+        cprime[j][1] = is0 ? sim1 : real;
+    }
+    sc r_star; sc_zero(&r_star);                                                         /* :1052-1056 */
+    for (int i = 0; i < ACT_L; i++) { sc p2; sc_pow2(&p2, i); sc_mul(&t, &s_i[i], &p2); sc_add(&r_star, &r_star, &t); }
+    sc k_prime, s_prime, nc; ge c_;
+    scalar_random(&k_prime, &rnd); scalar_random(&s_prime, &rnd);                        /* :1057-1058 */
+    sc_neg(&nc, &c_prime);
+    ge_table_mul(&t1, &P->h1, &nc); ge_table_mul(&t2, &P->h2, &k_prime); ge_add(&c_, &t1, &t2);
+    ge_table_mul(&t1, &P->h3, &s_prime); ge_add(&c_, &c_, &t1);                          /* :1059 */
+    static __thread transcript tr; sc gamma;
+    tr_new(&tr, P, "spend");                                                             /* :1061-1070 */
+    tr_add_scalar(&tr, &tk->k);
+    tr_add_element(&tr, &a_prime); tr_add_element(&tr, &b_bar);
+    tr_add_element(&tr, &a1); tr_add_element(&tr, &a2);
+    for (int j = 0; j < ACT_L; j++) tr_add_element(&tr, &sp->com[j]);
+    for (int j = 0; j < ACT_L; j++) { tr_add_element(&tr, &cprime[j][0]); tr_add_element(&tr, &cprime[j][1]); }
+    tr_add_element(&tr, &c_);
+    tr_challenge(&gamma, &tr);
+    sc ng; sc_neg(&ng, &gamma);
+    sc_mul(&t, &ng, &tk->e); sc_add(&sp->e_bar, &t, &e_prime);                           /* :1072 */
+    sc_mul(&t, &gamma, &r2); sc_add(&sp->r2_bar, &t, &r2_prime);                         /* :1073 */
+    sc_mul(&t, &gamma, &r3); sc_add(&sp->r3_bar, &t, &r3_prime);                         /* :1074 */
+    sc_mul(&t, &ng, &tk->c); sc_add(&sp->c_bar, &t, &c_prime);                           /* :1075 */
+    sc_mul(&t, &ng, &tk->r); sc_add(&sp->r_bar, &t, &r_prime);                           /* :1076 */
+    for (int j = 0; j < ACT_L; j++) {                                                    /* :1077-1120 */
+        int is0 = (bit[j] == 0);
+        sc g_minus, g00, g01, a, b2;
+        sc_sub(&g_minus, &gamma, &gamma_i[j]);
+        sc_csel(&g00, &gamma_i[j], &g_minus, is0);
+        sp->gamma0[j] = g00;
+        sc_sub(&g01, &gamma, &g00);
+        if (j == 0) {
+            sc_mul(&a, &g00, &k_star); sc_add(&a, &a, &k0_prime); sc_csel(&sp->w00, &w0, &a, is0);
+            sc_mul(&b2, &g01, &k_star); sc_add(&b2, &b2, &k0_prime); sc_csel(&sp->w01, &b2, &w0, is0);
+        }
+        sc_mul(&a, &g00, &s_i[j]); sc_add(&a, &a, &s_i_prime[j]); sc_csel(&sp->z[j][0], &zr[j], &a, is0);
+        sc_mul(&b2, &g01, &s_i[j]); sc_add(&b2, &b2, &s_i_prime[j]); sc_csel(&sp->z[j][1], &b2, &zr[j], is0);
+    }
+    sc_mul(&t, &gamma, &k_star); sc_add(&sp->k_bar, &t, &k_prime);                       /* :1121 */
+    sc_mul(&t, &gamma, &r_star); sc_add(&sp->s_bar, &t, &s_prime);                       /* :1122 */
+    sp->k = tk->k; sp->s = *s; sp->a_prime = a_prime; sp->b_bar = b_bar; sp->gamma = gamma;
+    *pr_k = k_star; *pr_r = r_star; *pr_m = m;                                           /* :1124-1128 */
+}
+
+/* ------------------------------------------------------------------------------------
+ * byte-level exported API (records as in include/act_engine.h; wire bytes in, wire bytes out)
+ * ---------------------------------------------------------------------------------- */
+#define EXPORT __attribute__((visibility("default")))
+
+typedef struct { act_params P; act_key key; u8 h_enc[3][32]; } act_o_ctx;
+
+EXPORT int act_o_params_derive(const char *org, const char *svc, const char *dep, const char *ver, u8 h[96]) {
+    oracle_init();
+    ge H[3];
+    if (params_points_new(H, org, svc, dep, ver)) return -1;
+    for (int i = 0; i < 3; i++) ristretto_encode(h + 32 * i, &H[i]);
+    return 0;
+}
+/* ctx from encoded H1..H3, secret x and public W (wire bytes). returns NULL on invalid point */
+EXPORT act_o_ctx *act_o_ctx_create(const u8 h[96], const u8 x[32], const u8 w[32]) {
+    oracle_init();
+    act_o_ctx *c = (act_o_ctx *)calloc(1, sizeof *c);
+    ge H[3];
+    for (int i = 0; i < 3; i++) if (!ristretto_decode(&H[i], h + 32 * i)) { free(c); return NULL; }
+    ge_table_create(&c->P.h1, &H[0]); ge_table_create(&c->P.h2, &H[1]); ge_table_create(&c->P.h3, &H[2]);
+    sc_from_bytes_mod_order(&c->key.x, x);
+    if (!ristretto_decode(&c->key.w, w)) { free(c); return NULL; }
+    memcpy(c->h_enc, h, 96);
+    return c;
+}
+EXPORT void act_o_ctx_destroy(act_o_ctx *c) { if (c) { memset(c, 0, sizeof *c); free(c); } }
+
+/* PrivateKey::random (src/lib.rs:188-194): x from 64 rng bytes, W = G*x */
+EXPORT void act_o_keygen(const u8 rnd[64], u8 x[32], u8 w[32]) {
+    oracle_init();
+    sc s; ge W; sc_from_bytes_wide(&s, rnd); ge_scalarmult(&W, &GE_BASE, &s);
+    sc_tobytes(x, &s); ristretto_encode(w, &W);
+}
+/* PreIssuance::random + request: pre = r||k (64 B, canonical scalars), rnd = 128 B, req = K||gamma||k_bar||r_bar */
+EXPORT void act_o_request(const act_o_ctx *c, const u8 pre[64], const u8 rnd[128], u8 req[128]) {
+    sc r, k; issuance_request rq;
+    sc_from_bytes_mod_order(&r, pre); sc_from_bytes_mod_order(&k, pre + 32);
+    act_request(&c->P, &r, &k, rnd, &rq);
+    ristretto_encode(req, &rq.K); sc_tobytes(req + 32, &rq.gamma); sc_tobytes(req + 64, &rq.k_bar); sc_tobytes(req + 96, &rq.r_bar);
+}
+EXPORT int act_o_issue(const act_o_ctx *c, const u8 req[128], const u8 cbytes[32], const u8 rnd[128], u8 resp[160]) {
+    issuance_request rq; issuance_response rs; sc cs;
+    memset(resp, 0, 160);
+    if (!ristretto_decode(&rq.K, req)) return ST_DECODE_INVALID_POINT;
+    sc_from_bytes_mod_order(&rq.gamma, req + 32); sc_from_bytes_mod_order(&rq.k_bar, req + 64);
+    sc_from_bytes_mod_order(&rq.r_bar, req + 96); sc_from_bytes_mod_order(&cs, cbytes);
+    int st = act_issue(&c->P, &c->key, &rq, &cs, rnd, &rs);
+    if (st) return st;
+    ristretto_encode(resp, &rs.A); sc_tobytes(resp + 32, &rs.e); sc_tobytes(resp + 64, &rs.gamma);
+    sc_tobytes(resp + 96, &rs.z); sc_tobytes(resp + 128, &rs.c);
+    return ST_OK;
+}
+EXPORT int act_o_issuance_check(const act_o_ctx *c, const u8 K[32], const u8 resp[160]) {
+    ge Kp; issuance_response rs;
+    if (!ristretto_decode(&Kp, K) || !ristretto_decode(&rs.A, resp)) return ST_DECODE_INVALID_POINT;
+    sc_from_bytes_mod_order(&rs.e, resp + 32); sc_from_bytes_mod_order(&rs.gamma, resp + 64);
+    sc_from_bytes_mod_order(&rs.z, resp + 96); sc_from_bytes_mod_order(&rs.c, resp + 128);
+    return act_issuance_check(&c->P, &c->key.w, &Kp, &rs);
+}
+/* packed SpendProof record, 526 x 32 B, SURVEY Appendix A:
+ * 0:k 1:s 2:A' 3:B 4..131:com 132:gamma 133:e 134:r2 135:r3 136:c 137:r 138:w00 139:w01 140..267:gamma0
+ * 268+2j+b: z[j][b] 524:k_bar 525:s_bar */
+#define PROOF_BYTES (526 * 32)
+static int proof_unpack(spend_proof *sp, const u8 *p) {
+#define SCAL(dst, idx) sc_from_bytes_mod_order(&(dst), p + 32 * (idx))
+    SCAL(sp->k, 0); SCAL(sp->s, 1);
+    if (!ristretto_decode(&sp->a_prime, p + 64)) return 0;
+    if (!ristretto_decode(&sp->b_bar, p + 96)) return 0;
+    for (int j = 0; j < ACT_L; j++) if (!ristretto_decode(&sp->com[j], p + 32 * (4 + j))) return 0;
+    SCAL(sp->gamma, 132); SCAL(sp->e_bar, 133); SCAL(sp->r2_bar, 134); SCAL(sp->r3_bar, 135);
+    SCAL(sp->c_bar, 136); SCAL(sp->r_bar, 137); SCAL(sp->w00, 138); SCAL(sp->w01, 139);
+    for (int j = 0; j < ACT_L; j++) SCAL(sp->gamma0[j], 140 + j);
+    for (int j = 0; j < ACT_L; j++) { SCAL(sp->z[j][0], 268 + 2 * j); SCAL(sp->z[j][1], 269 + 2 * j); }
+    SCAL(sp->k_bar, 524); SCAL(sp->s_bar, 525);
+#undef SCAL
+    return 1;
+}
+static void proof_pack(u8 *p, const spend_proof *sp) {
+#define SCAL(src, idx) sc_tobytes(p + 32 * (idx), &(src))
+    SCAL(sp->k, 0); SCAL(sp->s, 1);
+    ristretto_encode(p + 64, &sp->a_prime); ristretto_encode(p + 96, &sp->b_bar);
+    for (int j = 0; j < ACT_L; j++) ristretto_encode(p + 32 * (4 + j), &sp->com[j]);
+    SCAL(sp->gamma, 132); SCAL(sp->e_bar, 133); SCAL(sp->r2_bar, 134); SCAL(sp->r3_bar, 135);
+    SCAL(sp->c_bar, 136); SCAL(sp->r_bar, 137); SCAL(sp->w00, 138); SCAL(sp->w01, 139);
+    for (int j = 0; j < ACT_L; j++) SCAL(sp->gamma0[j], 140 + j);
+    for (int j = 0; j < ACT_L; j++) { SCAL(sp->z[j][0], 268 + 2 * j); SCAL(sp->z[j][1], 269 + 2 * j); }
+    SCAL(sp->k_bar, 524); SCAL(sp->s_bar, 525);
+#undef SCAL
+}
+/* token = A||e||k||r||c (160 B); s 32 B; rnd 524*64 B; proof 16832 B; prerefund = k*||r*||m (96 B) */
+EXPORT int act_o_prove_spend(const act_o_ctx *c, const u8 token[160], const u8 s[32], const u8 *rnd, u8 *proof, u8 prerefund[96]) {
+    credit_token tk; sc ss, pk, pr, pm;
+    spend_proof *sp = (spend_proof *)malloc(sizeof *sp);
+    if (!ristretto_decode(&tk.a, token)) { free(sp); return ST_DECODE_INVALID_POINT; }
+    sc_from_bytes_mod_order(&tk.e, token + 32); sc_from_bytes_mod_order(&tk.k, token + 64);
+    sc_from_bytes_mod_order(&tk.r, token + 96); sc_from_bytes_mod_order(&tk.c, token + 128);
+    sc_from_bytes_mod_order(&ss, s);
+    act_prove_spend(&c->P, &tk, &ss, rnd, sp, &pk, &pr, &pm);
+    proof_pack(proof, sp);
+    sc_tobytes(prerefund, &pk); sc_tobytes(prerefund + 32, &pr); sc_tobytes(prerefund + 64, &pm);
+    free(sp);
+    return ST_OK;
+}
+/* refund: proof 16832 B wire bytes; rnd 128 B; out refund = A*||e*||gamma||z (128 B), nullifier = reduced k.
+ * On any failure refund and nullifier are zero-filled. */
+EXPORT int act_o_refund(const act_o_ctx *c, const u8 *proof, const u8 rnd[128], u8 refund[128], u8 nullifier[32]) {
+    spend_proof *sp = (spend_proof *)malloc(sizeof *sp); refund_t rf;
+    memset(refund, 0, 128); memset(nullifier, 0, 32);
+    if (!proof_unpack(sp, proof)) { free(sp); return ST_DECODE_INVALID_POINT; }
+    int st = act_refund(&c->P, &c->key, sp, rnd, &rf);
+    if (st == ST_OK) {
+        ristretto_encode(refund, &rf.A); sc_tobytes(refund + 32, &rf.e); sc_tobytes(refund + 64, &rf.gamma);
+        sc_tobytes(refund + 96, &rf.z); sc_tobytes(nullifier, &sp->k);
+    }
+    free(sp);
+    return st;
+}
+EXPORT int act_o_refund_check(const act_o_ctx *c, const u8 *com /*4096*/, const u8 refund[128]) {
+    static __thread ge cm[ACT_L]; refund_t rf;
+    for (int j = 0; j < ACT_L; j++) if (!ristretto_decode(&cm[j], com + 32 * j)) return ST_DECODE_INVALID_POINT;
+    if (!ristretto_decode(&rf.A, refund)) return ST_DECODE_INVALID_POINT;
+    sc_from_bytes_mod_order(&rf.e, refund + 32); sc_from_bytes_mod_order(&rf.gamma, refund + 64);
+    sc_from_bytes_mod_order(&rf.z, refund + 96);
+    return act_refund_check(&c->P, &c->key.w, cm, &rf);
+}
+
+/* ---- primitives exported for cross-checks ---- */
+EXPORT int act_o_ristretto_decode_encode(const u8 in[32], u8 out[32]) {
+    oracle_init(); ge p;
+    if (!ristretto_decode(&p, in)) return 0;
+    ristretto_encode(out, &p); return 1;
+}
+EXPORT void act_o_ristretto_from_uniform(const u8 in[64], u8 out[32]) { oracle_init(); ge p; ristretto_from_uniform(&p, in); ristretto_encode(out, &p); }
+/* out = enc(s*P) by the variable-base path; P given encoded. returns 0 if P invalid */
+EXPORT int act_o_scalarmult(const u8 s[32], const u8 P[32], u8 out[32]) {
+    oracle_init(); ge p, q; sc k;
+    if (!ristretto_decode(&p, P)) return 0;
+    sc_from_bytes_mod_order(&k, s); ge_scalarmult(&q, &p, &k); ristretto_encode(out, &q); return 1;
+}
+EXPORT void act_o_scalarmult_base(const u8 s[32], u8 out[32]) {
+    oracle_init(); ge q; sc k; sc_from_bytes_mod_order(&k, s); ge_table_mul(&q, &GE_BASE_TABLE, &k); ristretto_encode(out, &q);
+}
+EXPORT int act_o_point_add(const u8 A[32], const u8 B[32], u8 out[32]) {
+    oracle_init(); ge a, b, r;
+    if (!ristretto_decode(&a, A) || !ristretto_decode(&b, B)) return 0;
+    ge_add(&r, &a, &b); ristretto_encode(out, &r); return 1;
+}
+EXPORT void act_o_blake3(const u8 *in, size_t n, u8 *out, size_t outlen) { blake3_xof(in, n, out, outlen); }
+EXPORT void act_o_sc_reduce32(const u8 in[32], u8 out[32]) { oracle_init(); sc a; sc_from_bytes_mod_order(&a, in); sc_tobytes(out, &a); }
+EXPORT void act_o_sc_reduce64(const u8 in[64], u8 out[32]) { oracle_init(); sc a; sc_from_bytes_wide(&a, in); sc_tobytes(out, &a); }
+EXPORT void act_o_sc_muladd(const u8 a[32], const u8 b[32], const u8 c[32], u8 out[32]) {
+    oracle_init(); sc x, y, z, r; sc_from_bytes_mod_order(&x, a); sc_from_bytes_mod_order(&y, b); sc_from_bytes_mod_order(&z, c);
+    sc_mul(&r, &x, &y); sc_add(&r, &r, &z); sc_tobytes(out, &r);
+}
+EXPORT void act_o_sc_invert(const u8 a[32], u8 out[32]) { oracle_init(); sc x, r; sc_from_bytes_mod_order(&x, a); sc_invert(&r, &x); sc_tobytes(out, &r); }
+/* Transcript::with(params, label, items) -> challenge; items = n x 32 B already-encoded payloads */
+EXPORT void act_o_transcript_challenge(const act_o_ctx *c, const char *label, const u8 *items, size_t n, u8 out[32]) {
+    static __thread transcript tr; sc g;
+    tr_new(&tr, &c->P, label);
+    for (size_t i = 0; i < n; i++) tr_update(&tr, items + 32 * i, 32);
+    tr_challenge(&g, &tr); sc_tobytes(out, &g);
+}
+/* field-level helpers so tests can pin fe arithmetic against python big ints */
+EXPORT void act_o_fe_mul(const u8 a[32], const u8 b[32], u8 out[32]) { fe x, y, z; fe_frombytes(&x, a); fe_frombytes(&y, b); fe_mul(&z, &x, &y); fe_tobytes(out, &z); }
+EXPORT void act_o_fe_invert(const u8 a[32], u8 out[32]) { fe x, z; fe_frombytes(&x, a); fe_invert(&z, &x); fe_tobytes(out, &z); }
+
+/* ------------------------------------------------------------------------------------
+ * batch drivers (one independent request per thread, contiguous ranges) -- used for the
+ * parity checker on batches and as the "restated-reference CPU baseline" timing leg.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    const act_o_ctx *c; int kind; size_t lo, hi;
+    const u8 *in, *in2, *rnd; u8 *out, *out2, *status;
+} batch_job;
+static void *batch_worker(void *arg) {
+    batch_job *j = (batch_job *)arg;
+    for (size_t i = j->lo; i < j->hi; i++) {
+        switch (j->kind) {
+        case 0: j->status[i] = (u8)act_o_issue(j->c, j->in + 128 * i, j->in2 + 32 * i, j->rnd + 128 * i, j->out + 160 * i); break;
+        case 1: j->status[i] = (u8)act_o_refund(j->c, j->in + (size_t)PROOF_BYTES * i, j->rnd + 128 * i, j->out + 128 * i, j->out2 + 32 * i); break;
+        case 2: j->status[i] = (u8)act_o_issuance_check(j->c, j->in + 32 * i, j->in2 + 160 * i); break;
+        case 3: j->status[i] = (u8)act_o_refund_check(j->c, j->in + 4096 * i, j->in2 + 128 * i); break;
+        }
+    }
+    return NULL;
+}
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+/* returns elapsed seconds */
+static double run_batch(const act_o_ctx *c, int kind, size_t n, int threads, const u8 *in, const u8 *in2, const u8 *rnd,
+                        u8 *out, u8 *out2, u8 *status) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n && n > 0) threads = (int)n;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    batch_job *jobs = (batch_job *)malloc(sizeof(batch_job) * threads);
+    double t0 = now_s();
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (batch_job){c, kind, n * t / threads, n * (t + 1) / threads, in, in2, rnd, out, out2, status};
+        pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    double t1 = now_s();
+    free(th); free(jobs);
+    return t1 - t0;
+}
+EXPORT double act_o_batch_issue(const act_o_ctx *c, size_t n, int threads, const u8 *req, const u8 *cs, const u8 *rnd, u8 *resp, u8 *status) {
+    return run_batch(c, 0, n, threads, req, cs, rnd, resp, NULL, status);
+}
+EXPORT double act_o_batch_refund(const act_o_ctx *c, size_t n, int threads, const u8 *proofs, const u8 *rnd, u8 *refunds, u8 *nullifiers, u8 *status) {
+    return run_batch(c, 1, n, threads, proofs, NULL, rnd, refunds, nullifiers, status);
+}
+EXPORT double act_o_batch_issuance_check(const act_o_ctx *c, size_t n, int threads, const u8 *K, const u8 *resp, u8 *status) {
+    return run_batch(c, 2, n, threads, K, resp, NULL, NULL, NULL, status);
+}
+EXPORT double act_o_batch_refund_check(const act_o_ctx *c, size_t n, int threads, const u8 *com, const u8 *refund, u8 *status) {
+    return run_batch(c, 3, n, threads, com, refund, NULL, NULL, NULL, status);
+}
+
+/* Timing leg that mirrors what benches/benchmark.rs:166-212 times: the typed refund() closure only
+ * (CBOR/point decode happens before the clock starts).  Proofs are decoded once, then each thread
+ * loops over its share `reps` times.  Returns elapsed seconds; *ok counts accepted refunds. */
+typedef struct { const act_o_ctx *c; spend_proof *sp; size_t lo, hi; int reps; const u8 *rnd; size_t ok; } typed_job;
+static void *typed_refund_worker(void *arg) {
+    typed_job *j = (typed_job *)arg; refund_t rf;
+    for (int r = 0; r < j->reps; r++)
+        for (size_t i = j->lo; i < j->hi; i++)
+            j->ok += act_refund(&j->c->P, &j->c->key, &j->sp[i], j->rnd + 128 * i, &rf) == ST_OK;
+    return NULL;
+}
+EXPORT double act_o_time_refund_typed(const act_o_ctx *c, size_t n, int threads, int reps, const u8 *proofs, const u8 *rnd, size_t *ok) {
+    spend_proof *sp = (spend_proof *)malloc(sizeof(spend_proof) * n);
+    for (size_t i = 0; i < n; i++) if (!proof_unpack(&sp[i], proofs + (size_t)PROOF_BYTES * i)) { free(sp); return -1.0; }
+    if ((size_t)threads > n) threads = (int)n;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    typed_job *jobs = (typed_job *)calloc(threads, sizeof(typed_job));
+    double t0 = now_s();
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (typed_job){c, sp, n * t / threads, n * (t + 1) / threads, reps, rnd, 0};
+        pthread_create(&th[t], NULL, typed_refund_worker, &jobs[t]);
+    }
+    size_t tot = 0;
+    for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); tot += jobs[t].ok; }
+    double t1 = now_s();
+    if (ok) *ok = tot;
+    free(th); free(jobs); free(sp);
+    return t1 - t0;
+}
+typedef struct { const act_o_ctx *c; issuance_request *rq; sc *cs; size_t lo, hi; int reps; const u8 *rnd; size_t ok; } typed_ijob;
+static void *typed_issue_worker(void *arg) {
+    typed_ijob *j = (typed_ijob *)arg; issuance_response rs;
+    for (int r = 0; r < j->reps; r++)
+        for (size_t i = j->lo; i < j->hi; i++)
+            j->ok += act_issue(&j->c->P, &j->c->key, &j->rq[i], &j->cs[i], j->rnd + 128 * i, &rs) == ST_OK;
+    return NULL;
+}
+/* mirrors benches/benchmark.rs:50-78 (typed issue() closure) */
+EXPORT double act_o_time_issue_typed(const act_o_ctx *c, size_t n, int threads, int reps, const u8 *req, const u8 *cs, const u8 *rnd, size_t *ok) {
+    issuance_request *rq = (issuance_request *)malloc(sizeof(issuance_request) * n);
+    sc *cc = (sc *)malloc(sizeof(sc) * n);
+    for (size_t i = 0; i < n; i++) {
+        if (!ristretto_decode(&rq[i].K, req + 128 * i)) { free(rq); free(cc); return -1.0; }
+        sc_from_bytes_mod_order(&rq[i].gamma, req + 128 * i + 32); sc_from_bytes_mod_order(&rq[i].k_bar, req + 128 * i + 64);
+        sc_from_bytes_mod_order(&rq[i].r_bar, req + 128 * i + 96); sc_from_bytes_mod_order(&cc[i], cs + 32 * i);
+    }
+    if ((size_t)threads > n) threads = (int)n;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    typed_ijob *jobs = (typed_ijob *)calloc(threads, sizeof(typed_ijob));
+    double t0 = now_s();
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (typed_ijob){c, rq, cc, n * t / threads, n * (t + 1) / threads, reps, rnd, 0};
+        pthread_create(&th[t], NULL, typed_issue_worker, &jobs[t]);
+    }
+    size_t tot = 0;
+    for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); tot += jobs[t].ok; }
+    double t1 = now_s();
+    if (ok) *ok = tot;
+    free(th); free(jobs); free(rq); free(cc);
+    return t1 - t0;
+}
+
+/* Fixture generation at scale: n independent issue->token->prove_spend trips, multi-threaded.
+ * seeds: per-item 64-byte seeds; all randomness for item i is BLAKE3-XOF(seed_i).
+ * c_i (credits) and s_i (charge) given as u64.  Outputs: requests (n*128), cs (n*32), responses(n*160),
+ * proofs (n*16832).  Used by tests and bench to synthesise valid inputs. */
+typedef struct { const act_o_ctx *c; size_t lo, hi; const u8 *seeds; const u64 *credits, *charges; u8 *req, *cs, *resp, *proofs, *prerefund; } gen_job;
+static void *gen_worker(void *arg) {
+    gen_job *j = (gen_job *)arg;
+    u8 *rnd = (u8 *)malloc(64 * (2 + 2 + 2 + 524));
+    for (size_t i = j->lo; i < j->hi; i++) {
+        blake3_xof(j->seeds + 64 * i, 64, rnd, 64 * (2 + 2 + 2 + 524));
+        sc r, k, cc; u8 pre[64], req[128], cb[32], resp[160], token[160], sb[32], pr[96];
+        sc_from_bytes_wide(&r, rnd); sc_from_bytes_wide(&k, rnd + 64);
+        sc_tobytes(pre, &r); sc_tobytes(pre + 32, &k);
+        act_o_request(j->c, pre, rnd + 128, req);
+        sc_from_u64(&cc, j->credits[i]); sc_tobytes(cb, &cc);
+        act_o_issue(j->c, req, cb, rnd + 256, resp);
+        memcpy(token, resp, 64); memcpy(token + 64, pre + 32, 32); memcpy(token + 96, pre, 32); memcpy(token + 128, cb, 32);
+        sc_from_u64(&cc, j->charges[i]); sc_tobytes(sb, &cc);
+        if (j->req) memcpy(j->req + 128 * i, req, 128);
+        if (j->cs) memcpy(j->cs + 32 * i, cb, 32);
+        if (j->resp) memcpy(j->resp + 160 * i, resp, 160);
+        if (j->proofs) act_o_prove_spend(j->c, token, sb, rnd + 384, j->proofs + (size_t)PROOF_BYTES * i, pr);
+        if (j->prerefund) memcpy(j->prerefund + 96 * i, pr, 96);
+    }
+    free(rnd);
+    return NULL;
+}
+EXPORT void act_o_generate(const act_o_ctx *c, size_t n, int threads, const u8 *seeds, const u64 *credits, const u64 *charges,
+                           u8 *req, u8 *cs, u8 *resp, u8 *proofs, u8 *prerefund) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n && n > 0) threads = (int)n;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    gen_job *jobs = (gen_job *)malloc(sizeof(gen_job) * threads);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (gen_job){c, n * t / threads, n * (t + 1) / threads, seeds, credits, charges, req, cs, resp, proofs, prerefund};
+        pthread_create(&th[t], NULL, gen_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+}
