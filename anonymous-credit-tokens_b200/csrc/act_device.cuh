@@ -1,0 +1,591 @@
+// act_device.cuh -- per-thread bodies of the batch kernels: scalar multiplication strategies,
+// transcript assembly, and the issue / refund / to_credit_token equations.
+//
+// Every `*_thread` function is the whole body of one CUDA thread of the kernel of the same name in
+// act_kernels.cu; they are plain functions of (context, index, buffers) so that tests/hostsim can
+// run the identical logic on the CPU for small cases.  Reference equations: /root/reference
+// src/lib.rs:621-663 (issue), :781-869 (refund), :528-562 and :1217-1253 (client checks),
+// src/transcript.rs:54-155 (transcript layout).
+//
+// Secret-dependent work (x, alpha, (e+x)^-1) uses the *_ct routines: signed fixed windows, table
+// selection by a full masked scan, no secret-dependent branch or address.  Public data (everything
+// in a proof, gamma, e) uses direct table indexing.
+#pragma once
+#include "blake3.cuh"
+#include "fe25519.cuh"
+#include "ge25519.cuh"
+#include "sc25519.cuh"
+
+// ---- status codes (include/act_engine.h) ----------------------------------------------------------
+#define ACT_ST_OK 0
+#define ACT_ST_INVALID_ISSUANCE_REQUEST_PROOF 1
+#define ACT_ST_INVALID_ISSUANCE_RESPONSE_PROOF 2
+#define ACT_ST_INVALID_REFUND_PROOF 4
+#define ACT_ST_IDENTITY_POINT 6
+#define ACT_ST_INVALID_CLIENT_SPEND_PROOF 7
+#define ACT_ST_DECODE_INVALID_POINT 0x81
+
+#define ACT_FLAG_BAD_POINT 1u
+#define ACT_FLAG_IDENTITY 2u
+#define ACT_FLAG_BAD_PROOF 4u
+
+// ---- layout constants -----------------------------------------------------------------------------
+#define ACT_L 128
+#define ACT_PROOF_WORDS (526 * 8)
+#define ACT_ITEMS 390               // "spend" transcript items: k, A', B, A1, A2, com[128], C'[128][2], C
+#define ACT_ITEM_WORDS (ACT_ITEMS * 8)
+#define ACT_SPEND_BYTES 15784u      // 184 + 40*390
+#define ACT_SPEND_CHUNKS 16
+
+// fixed-base tables: signed radix-256, 32 windows, entry |d| in 0..128 (0 = identity), affine Niels
+#define ACT_FB_WIN 32
+#define ACT_FB_ENT 129
+#define ACT_FB_SIZE (ACT_FB_WIN * ACT_FB_ENT)
+// constant-time basepoint table: signed radix-16, 64 windows, |d| in 0..8
+#define ACT_CT_WIN 64
+#define ACT_CT_ENT 9
+#define ACT_CT_SIZE (ACT_CT_WIN * ACT_CT_ENT)
+
+#define ACT_BASE_G 0
+#define ACT_BASE_H1 1
+#define ACT_BASE_H2 2
+#define ACT_BASE_H3 3
+
+struct act_ctx {
+    const ge_niels* fb[4];   // vartime fixed-base tables for G, H1, H2, H3 (global memory, L2 resident)
+    const ge_niels* ct_g;    // constant-time table for G
+    sc x;                    // issuer secret
+    ge W;                    // issuer public key
+    u32 h_enc[3][8];         // encodings of H1..H3
+    u32 prefix[4][48];       // transcript prefixes "request","respond","refund","spend" as LE words, zero padded
+    u32 prefix_len[4];       // 186, 186, 185, 184 bytes
+};
+#define ACT_TR_REQUEST 0
+#define ACT_TR_RESPOND 1
+#define ACT_TR_REFUND 2
+#define ACT_TR_SPEND 3
+
+#if ACT_PTX
+#define ACT_ATOMIC_OR(p, v) atomicOr((p), (v))
+#else
+#define ACT_ATOMIC_OR(p, v) (*(p) |= (v))
+#endif
+
+// ---- 32-byte loads/stores ---------------------------------------------------------------------------
+ACT_FN void load8(u32* w, const u32* p) {
+#if ACT_PTX
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) w[i] = p[i];
+#endif
+}
+ACT_FN void store8(u32* p, const u32* w) {
+#if ACT_PTX
+    reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+#else
+    for (int i = 0; i < 8; i++) p[i] = w[i];
+#endif
+}
+ACT_FN void store8_zero(u32* p) {
+    u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    store8(p, z);
+}
+ACT_FN sc load_scalar(const u32* p) { u32 w[8]; load8(w, p); return sc_from_words(w); }
+ACT_FN void store_scalar(u32* p, const sc& s) { store8(p, s.v); }
+ACT_FN u32 load_point(ge* out, const u32* p) { u32 w[8]; load8(w, p); return ristretto_decode_(out, w); }
+ACT_FN void store_point(u32* p, const ge& q) { u32 w[8]; ristretto_encode_(w, &q); store8(p, w); }
+ACT_FN void load_fe(fe* f, const u32* p) { load8(f->v, p); }
+ACT_FN void store_fe(u32* p, const fe& f) { store8(p, f.v); }
+ACT_FN ge_niels load_niels(const ge_niels* p) {
+    ge_niels r;
+    const u32* q = reinterpret_cast<const u32*>(p);
+    load8(r.ypx.v, q); load8(r.ymx.v, q + 8); load8(r.xy2d.v, q + 16);
+    return r;
+}
+
+// ---- fixed-base accumulation (public scalars) ---------------------------------------------------------
+// acc += (negate ? -s : s) * B using the radix-256 table of B: 32 mixed additions, no doublings.
+ACT_FN ge fb_accumulate(ge acc, const ge_niels* tab, const sc& s, bool negate) {
+    sc b = sc_bias<8>(s);
+    ACT_NOUNROLL for (int i = 0; i < ACT_FB_WIN; i++) {
+        int d = sc_digit<8>(b, i);
+        u32 neg = (d < 0) ? 1u : 0u;
+        u32 idx = (u32)(d < 0 ? -d : d);
+        if (negate) neg ^= 1u;
+        ge_niels e = load_niels(tab + i * ACT_FB_ENT + idx);
+        acc = ge_add_niels(acc, ge_niels_cneg(e, neg));
+    }
+    return acc;
+}
+// acc += alpha * G with a secret alpha: radix-16, all 9 entries of each window scanned
+ACT_FN ge fb_accumulate_ct(ge acc, const ge_niels* tab, const sc& s) {
+    sc b = sc_bias<4>(s);
+    ACT_NOUNROLL for (int i = 0; i < ACT_CT_WIN; i++) {
+        int d = sc_digit<4>(b, i);
+        u32 neg = ((u32)d) >> 31;
+        u32 idx = (u32)((d ^ (d >> 31)) - (d >> 31));
+        ge_niels e = ge_niels_identity();
+        ACT_NOUNROLL for (u32 k = 1; k < ACT_CT_ENT; k++) {
+            ge_niels t = load_niels(tab + i * ACT_CT_ENT + k);
+            u32 hit = (idx == k);
+            e.ypx = fe_select(e.ypx, t.ypx, hit); e.ymx = fe_select(e.ymx, t.ymx, hit); e.xy2d = fe_select(e.xy2d, t.xy2d, hit);
+        }
+        acc = ge_add_niels(acc, ge_niels_cneg(e, neg));
+    }
+    return acc;
+}
+
+// ---- variable-base: signed radix-16 windows over a per-thread table of 0..8 multiples -------------------
+struct vb_table { ge_cached e[9]; };
+
+ACT_FN void vb_table_build(vb_table* t, const ge& P) {
+    t->e[0] = ge_cached_identity();
+    t->e[1] = ge_to_cached(P);
+    ge Q = P;
+    ACT_NOUNROLL for (int k = 2; k <= 8; k++) {
+        Q = ge_add_cached(Q, t->e[1]);
+        t->e[k] = ge_to_cached(Q);
+    }
+}
+ACT_FN ge_cached vb_lookup(const vb_table* t, int d, bool negate) {
+    u32 neg = (d < 0) ? 1u : 0u;
+    u32 idx = (u32)(d < 0 ? -d : d);
+    if (negate) neg ^= 1u;
+    return ge_cached_cneg(t->e[idx], neg);
+}
+ACT_FN ge_cached vb_lookup_ct(const vb_table* t, int d) {
+    u32 neg = ((u32)d) >> 31;
+    u32 idx = (u32)((d ^ (d >> 31)) - (d >> 31));
+    ge_cached e = ge_cached_identity();
+    ACT_NOUNROLL for (u32 k = 1; k <= 8; k++) {
+        u32 hit = (idx == k);
+        e.YpX = fe_select(e.YpX, t->e[k].YpX, hit); e.YmX = fe_select(e.YmX, t->e[k].YmX, hit);
+        e.Z = fe_select(e.Z, t->e[k].Z, hit); e.T2d = fe_select(e.T2d, t->e[k].T2d, hit);
+    }
+    return ge_cached_cneg(e, neg);
+}
+// sum_k (neg_k ? -s_k : s_k) * P_k for N public scalars sharing one doubling chain (Straus)
+template <int N>
+ACT_FN ge vb_mul_multi(const vb_table* t, const sc* s, const bool* negate) {
+    sc b[N];
+    ACT_UNROLL for (int k = 0; k < N; k++) b[k] = sc_bias<4>(s[k]);
+    ge acc = ge_identity();
+    ACT_NOUNROLL for (int i = 63; i >= 0; i--) {
+        if (i != 63) {
+            acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true);
+        }
+        ACT_UNROLL for (int k = 0; k < N; k++) acc = ge_add_cached(acc, vb_lookup(&t[k], sc_digit<4>(b[k], i), negate[k]));
+    }
+    return acc;
+}
+ACT_FN ge vb_mul(const vb_table* t, const sc& s, bool negate) { return vb_mul_multi<1>(t, &s, &negate); }
+// s * P for a secret s
+ACT_NOINLINE void vb_mul_ct_(ge* out, const ge* P, const sc* s) {
+    vb_table t;
+    vb_table_build(&t, *P);
+    sc b = sc_bias<4>(*s);
+    ge acc = ge_identity();
+    ACT_NOUNROLL for (int i = 63; i >= 0; i--) {
+        if (i != 63) {
+            acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true);
+        }
+        acc = ge_add_cached(acc, vb_lookup_ct(&t, sc_digit<4>(b, i)));
+    }
+    *out = acc;
+}
+
+// ---- single-chunk transcripts ---------------------------------------------------------------------------
+struct tr_small { u32 buf[128]; u32 len; };  // up to 512 bytes
+
+ACT_FN void tr_init(tr_small* t, const act_ctx* C, int which) {
+    ACT_NOUNROLL for (int i = 0; i < 128; i++) t->buf[i] = (i < 48) ? C->prefix[which][i] : 0u;
+    t->len = C->prefix_len[which];
+}
+ACT_FN void tr_put_word(tr_small* t, u32 w) {
+    u32 sh = (t->len & 3u) * 8u, idx = t->len >> 2;
+    t->buf[idx] |= w << sh;
+    if (sh) t->buf[idx + 1] |= w >> (32u - sh);
+    t->len += 4;
+}
+// Transcript::update with a 32-byte payload: u64be(32) || payload  (src/transcript.rs:95-98)
+ACT_FN void tr_add32(tr_small* t, const u32* w) {
+    tr_put_word(t, 0u);
+    tr_put_word(t, 0x20000000u);
+    ACT_NOUNROLL for (int i = 0; i < 8; i++) tr_put_word(t, w[i]);
+}
+ACT_FN sc tr_challenge(tr_small* t) {
+    u32 o[16];
+    b3_hash_single_chunk(t->buf, t->len, o);
+    return sc_from_wide(o);
+}
+
+// =============================================================================================================
+// BBS signing tail shared by issue and refund (src/lib.rs:643-662 and :846-868)
+// =============================================================================================================
+// X_A given; rnd = 32 words (e_wide || alpha_wide).  kind = ACT_TR_RESPOND (c, e, points) or ACT_TR_REFUND (e, points).
+// Writes A (8 words), e, gamma, z.
+ACT_NOINLINE void bbs_sign_(const act_ctx* C, const ge* X_A, const u32* rnd, int kind, const sc* c,
+                            u32* A_enc, sc* e_out, sc* gamma_out, sc* z_out) {
+    sc e = sc_from_wide(rnd);
+    sc ex = sc_add(e, C->x);
+    sc inv = sc_invert(ex);
+    ge A;
+    vb_mul_ct_(&A, X_A, &inv);                                   // A = X_A * (e+x)^-1        [secret scalar]
+    ge X_G = fb_accumulate(C->W, C->fb[ACT_BASE_G], e, false);   // X_G = G*e + W             [e is public output]
+    sc alpha = sc_from_wide(rnd + 16);
+    ge Y_A;
+    vb_mul_ct_(&Y_A, &A, &alpha);                                // Y_A = A * alpha           [secret scalar]
+    ge Y_G = fb_accumulate_ct(ge_identity(), C->ct_g, alpha);    // Y_G = G * alpha           [secret scalar]
+    tr_small tr;
+    tr_init(&tr, C, kind);
+    if (kind == ACT_TR_RESPOND) tr_add32(&tr, c->v);
+    tr_add32(&tr, e.v);
+    u32 w[8];
+    ristretto_encode_(A_enc, &A); tr_add32(&tr, A_enc);
+    ristretto_encode_(w, X_A); tr_add32(&tr, w);
+    ristretto_encode_(w, &X_G); tr_add32(&tr, w);
+    ristretto_encode_(w, &Y_A); tr_add32(&tr, w);
+    ristretto_encode_(w, &Y_G); tr_add32(&tr, w);
+    sc gamma = tr_challenge(&tr);
+    *e_out = e; *gamma_out = gamma;
+    *z_out = sc_add(sc_mul(gamma, ex), alpha);                   // z = gamma*(x+e) + alpha
+}
+
+// =============================================================================================================
+// issue (src/lib.rs:621-663).  req: n x 32 words (K, gamma, k_bar, r_bar); cs: n x 8; rnd: n x 32;
+// resp: n x 40 words (A, e, gamma, z, c); status: n bytes.
+// =============================================================================================================
+ACT_FN void issue_thread(const act_ctx* C, size_t i, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status) {
+    const u32* rq = req + 32 * i;
+    u32* out = resp + 40 * i;
+    u32 kw[8];
+    load8(kw, rq);
+    ge K;
+    u32 valid = ristretto_decode_(&K, kw);
+    sc gamma = load_scalar(rq + 8), k_bar = load_scalar(rq + 16), r_bar = load_scalar(rq + 24);
+    u32 st = ACT_ST_OK;
+    if (!valid) st = ACT_ST_DECODE_INVALID_POINT;
+    // K1 = h2*k_bar + h3*r_bar - K*gamma                                                     (:629-630)
+    vb_table tk;
+    vb_table_build(&tk, K);
+    ge K1 = vb_mul(&tk, gamma, true);
+    K1 = fb_accumulate(K1, C->fb[ACT_BASE_H2], k_bar, false);
+    K1 = fb_accumulate(K1, C->fb[ACT_BASE_H3], r_bar, false);
+    {
+        tr_small tr;
+        u32 w[8];
+        tr_init(&tr, C, ACT_TR_REQUEST);                                                  // (:633-635)
+        tr_add32(&tr, kw);  // canonical decode => compress(K) == wire bytes
+        ristretto_encode_(w, &K1); tr_add32(&tr, w);
+        sc g2 = tr_challenge(&tr);
+        if (st == ACT_ST_OK && !sc_eq(g2, gamma)) st = ACT_ST_INVALID_ISSUANCE_REQUEST_PROOF;   // (:638-640)
+    }
+    if (st != ACT_ST_OK) {
+        ACT_NOUNROLL for (int k = 0; k < 5; k++) store8_zero(out + 8 * k);
+        status[i] = (u8)st;
+        return;
+    }
+    sc c = load_scalar(cs + 8 * i);
+    // X_A = G + h1*c + K                                                                      (:644)
+    ge X_A = ge_add(K, ge_basepoint());
+    X_A = fb_accumulate(X_A, C->fb[ACT_BASE_H1], c, false);
+    u32 A_enc[8];
+    sc e, g, z;
+    u32 r[32];
+    ACT_NOUNROLL for (int k = 0; k < 4; k++) load8(r + 8 * k, rnd + 32 * i + 8 * k);
+    bbs_sign_(C, &X_A, r, ACT_TR_RESPOND, &c, A_enc, &e, &g, &z);
+    store8(out, A_enc); store_scalar(out + 8, e); store_scalar(out + 16, g); store_scalar(out + 24, z); store_scalar(out + 32, c);
+    status[i] = ACT_ST_OK;
+}
+
+// =============================================================================================================
+// PreIssuance::to_credit_token verification (src/lib.rs:528-562).  K: n x 8 words, resp: n x 40 words.
+// All inputs are public to the verifier.
+// =============================================================================================================
+// Y_A = A*z - X_A*gamma, Y_G = G*z - X_G*gamma, then the challenge over (scalars..., A, X_A, X_G, Y_A, Y_G)
+ACT_NOINLINE u32 dleq_check_(const act_ctx* C, int kind, const sc* c, const sc* e, const sc* gamma, const sc* z,
+                             const u32* A_words, const ge* A, const ge* X_A) {
+    ge X_G = fb_accumulate(C->W, C->fb[ACT_BASE_G], *e, false);
+    vb_table t[2];
+    vb_table_build(&t[0], *A);
+    vb_table_build(&t[1], *X_A);
+    sc ss[2] = {*z, *gamma};
+    bool ng[2] = {false, true};
+    ge Y_A = vb_mul_multi<2>(t, ss, ng);
+    vb_table_build(&t[0], X_G);
+    ge Y_G = vb_mul(&t[0], *gamma, true);
+    Y_G = fb_accumulate(Y_G, C->fb[ACT_BASE_G], *z, false);
+    tr_small tr;
+    u32 w[8];
+    tr_init(&tr, C, kind);
+    if (kind == ACT_TR_RESPOND) tr_add32(&tr, c->v);
+    tr_add32(&tr, e->v);
+    tr_add32(&tr, A_words);
+    ristretto_encode_(w, X_A); tr_add32(&tr, w);
+    ristretto_encode_(w, &X_G); tr_add32(&tr, w);
+    ristretto_encode_(w, &Y_A); tr_add32(&tr, w);
+    ristretto_encode_(w, &Y_G); tr_add32(&tr, w);
+    sc g2 = tr_challenge(&tr);
+    return sc_eq(g2, *gamma);
+}
+ACT_FN void issuance_check_thread(const act_ctx* C, size_t i, const u32* Kin, const u32* resp, u8* status) {
+    const u32* rs = resp + 40 * i;
+    ge K, A;
+    u32 aw[8];
+    load8(aw, rs);
+    u32 valid = load_point(&K, Kin + 8 * i) & ristretto_decode_(&A, aw);
+    sc e = load_scalar(rs + 8), gamma = load_scalar(rs + 16), z = load_scalar(rs + 24), c = load_scalar(rs + 32);
+    ge X_A = ge_add(K, ge_basepoint());                                                   // (:536)
+    X_A = fb_accumulate(X_A, C->fb[ACT_BASE_H1], c, false);
+    u32 ok = dleq_check_(C, ACT_TR_RESPOND, &c, &e, &gamma, &z, aw, &A, &X_A);            // (:537-552)
+    status[i] = (u8)(!valid ? ACT_ST_DECODE_INVALID_POINT : (ok ? ACT_ST_OK : ACT_ST_INVALID_ISSUANCE_RESPONSE_PROOF));
+}
+
+// =============================================================================================================
+// spend verification, stage 1: the 256 range-proof commitments (src/lib.rs:800-817).
+// One thread per (proof, j).  Writes items 5+j (com_j bytes), 133+2j, 134+2j (C'_j0, C'_j1) and the
+// affine-Niels form of com_j for the K' Horner chain in stage 2.
+// =============================================================================================================
+ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* proofs, u32* items, u32* com_niels, u32* flags) {
+    const u32* pf = proofs + (size_t)ACT_PROOF_WORDS * p;
+    u32* it = items + (size_t)ACT_ITEM_WORDS * p;
+    u32 cw[8];
+    load8(cw, pf + 8 * (4 + j));
+    ge P;
+    u32 valid = ristretto_decode_(&P, cw);
+    if (!valid) ACT_ATOMIC_OR(&flags[p], ACT_FLAG_BAD_POINT);
+    store8(it + 8 * (5 + j), cw);
+    {
+        ge_niels n = ge_affine_to_niels(P.X, P.Y);
+        u32* cn = com_niels + ((size_t)ACT_L * p + j) * 24;
+        store_fe(cn, n.ypx); store_fe(cn + 8, n.ymx); store_fe(cn + 16, n.xy2d);
+    }
+    sc gamma = load_scalar(pf + 8 * 132);
+    sc g0 = load_scalar(pf + 8 * (140 + j));
+    sc g1 = sc_sub(gamma, g0);                                                             // gamma01[j]  (:801,811)
+    sc z0 = load_scalar(pf + 8 * (268 + 2 * j)), z1 = load_scalar(pf + 8 * (269 + 2 * j));
+    vb_table t;
+    vb_table_build(&t, P);
+    // C'_j0 = [h2*w00 +] h3*z_j0 - com_j*gamma0_j                                          (:806-807,814-815)
+    ge Q = vb_mul(&t, g0, true);
+    Q = fb_accumulate(Q, C->fb[ACT_BASE_H3], z0, false);
+    if (j == 0) Q = fb_accumulate(Q, C->fb[ACT_BASE_H2], load_scalar(pf + 8 * 138), false);
+    store_point(it + 8 * (133 + 2 * j), Q);
+    // C'_j1 = [h2*w01 +] h3*z_j1 - (com_j - h1)*gamma01_j = ... + h1*gamma01_j - com_j*gamma01_j   (:808-809,816)
+    Q = vb_mul(&t, g1, true);
+    Q = fb_accumulate(Q, C->fb[ACT_BASE_H3], z1, false);
+    Q = fb_accumulate(Q, C->fb[ACT_BASE_H1], g1, false);
+    if (j == 0) Q = fb_accumulate(Q, C->fb[ACT_BASE_H2], load_scalar(pf + 8 * 139), false);
+    store_point(it + 8 * (134 + 2 * j), Q);
+}
+
+// =============================================================================================================
+// spend verification, stage 2: one thread per proof.  A-bar (secret x), A1, A2, K' (Horner), C
+// (src/lib.rs:787-799, 819-829).  Writes items 0..4 and 389, K' for the signing tail.
+// =============================================================================================================
+ACT_FN void spend_head_thread(const act_ctx* C, size_t p, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
+    const u32* pf = proofs + (size_t)ACT_PROOF_WORDS * p;
+    u32* it = items + (size_t)ACT_ITEM_WORDS * p;
+    u32 aw[8], bw[8];
+    load8(aw, pf + 16); load8(bw, pf + 24);
+    ge Ap, Bb;
+    u32 valid = ristretto_decode_(&Ap, aw) & ristretto_decode_(&Bb, bw);
+    u32 fl = 0;
+    if (!valid) fl |= ACT_FLAG_BAD_POINT;
+    if (ristretto_is_identity(Ap)) fl |= ACT_FLAG_IDENTITY;                                // (:787-789)
+    if (fl) ACT_ATOMIC_OR(&flags[p], fl);
+    sc k = load_scalar(pf), s = load_scalar(pf + 8), gamma = load_scalar(pf + 8 * 132);
+    sc e_bar = load_scalar(pf + 8 * 133), r2_bar = load_scalar(pf + 8 * 134), r3_bar = load_scalar(pf + 8 * 135);
+    sc c_bar = load_scalar(pf + 8 * 136), r_bar = load_scalar(pf + 8 * 137);
+    sc k_bar = load_scalar(pf + 8 * 524), s_bar = load_scalar(pf + 8 * 525);
+    store_scalar(it, k);               // transcript.add_scalar(&k): reduced bytes          (:832)
+    store8(it + 8, aw); store8(it + 16, bw);
+    vb_table t[3];
+    {
+        ge Abar;
+        vb_mul_ct_(&Abar, &Ap, &C->x);                                                     // (:791) secret x
+        // A1 = A'*e_bar + B*r2_bar - Abar*gamma                                           (:793-795)
+        vb_table_build(&t[0], Ap); vb_table_build(&t[1], Bb); vb_table_build(&t[2], Abar);
+        sc ss[3] = {e_bar, r2_bar, gamma};
+        bool ng[3] = {false, false, true};
+        ge A1 = vb_mul_multi<3>(t, ss, ng);
+        store_point(it + 24, A1);
+    }
+    {
+        // A2 = B*r3_bar + h1*c_bar + h3*r_bar - (G + h2*k)*gamma                          (:792,796-799)
+        ge A2 = vb_mul(&t[1], r3_bar, false);
+        A2 = fb_accumulate(A2, C->fb[ACT_BASE_H1], c_bar, false);
+        A2 = fb_accumulate(A2, C->fb[ACT_BASE_H3], r_bar, false);
+        A2 = fb_accumulate(A2, C->fb[ACT_BASE_G], gamma, true);
+        A2 = fb_accumulate(A2, C->fb[ACT_BASE_H2], sc_mul(k, gamma), true);
+        store_point(it + 32, A2);
+    }
+    // K' = sum 2^i com_i by Horner from the top (the reference does 128 scalar mults, :819-824)
+    ge Kp = ge_identity();
+    const ge_niels* cn = reinterpret_cast<const ge_niels*>(com_niels) + (size_t)ACT_L * p;
+    ACT_NOUNROLL for (int i = ACT_L - 1; i >= 0; i--) {
+        Kp = ge_dbl(Kp, true);
+        Kp = ge_add_niels(Kp, load_niels(cn + i));
+    }
+    {
+        u32* kp = kprime + 32 * p;
+        store_fe(kp, Kp.X); store_fe(kp + 8, Kp.Y); store_fe(kp + 16, Kp.Z); store_fe(kp + 24, Kp.T);
+    }
+    {
+        // C = h1*(-c_bar) + h2*k_bar + h3*s_bar - (h1*s + K')*gamma                       (:825-829)
+        vb_table_build(&t[0], Kp);
+        ge Cc = vb_mul(&t[0], gamma, true);
+        Cc = fb_accumulate(Cc, C->fb[ACT_BASE_H1], sc_add(c_bar, sc_mul(s, gamma)), true);
+        Cc = fb_accumulate(Cc, C->fb[ACT_BASE_H2], k_bar, false);
+        Cc = fb_accumulate(Cc, C->fb[ACT_BASE_H3], s_bar, false);
+        store_point(it + 8 * 389, Cc);
+    }
+}
+
+// =============================================================================================================
+// spend verification, stage 3: BLAKE3 over the 15 784-byte transcript.  One thread per (proof, chunk)
+// produces the chunk chaining value; one thread per proof folds the 16 CVs and compares with gamma.
+// =============================================================================================================
+ACT_FN u32 spend_tr_word(const act_ctx* C, const u32* it, u32 g) {
+    if (g < 46u) return C->prefix[ACT_TR_SPEND][g];
+    u32 q = g - 46u;
+    if (q >= 10u * ACT_ITEMS) return 0u;
+    u32 item = q / 10u, o = q - item * 10u;
+    if (o == 0u) return 0u;
+    if (o == 1u) return 0x20000000u;
+    return it[item * 8u + o - 2u];
+}
+ACT_FN void spend_chunk_thread(const act_ctx* C, size_t p, int c, const u32* items, u32* cvs) {
+    const u32* it = items + (size_t)ACT_ITEM_WORDS * p;
+    u32 cv[8], m[16], o[16];
+    ACT_UNROLL for (int i = 0; i < 8; i++) cv[i] = B3_IV_[i];
+    u32 nbytes = (c == ACT_SPEND_CHUNKS - 1) ? (ACT_SPEND_BYTES - 1024u * (ACT_SPEND_CHUNKS - 1)) : 1024u;
+    u32 nblocks = (nbytes + 63u) / 64u;
+    ACT_NOUNROLL for (u32 b = 0; b < nblocks; b++) {
+        ACT_UNROLL for (int i = 0; i < 16; i++) m[i] = spend_tr_word(C, it, (u32)c * 256u + b * 16u + i);
+        u32 flags = (b == 0 ? B3_CHUNK_START : 0u), blen = 64;
+        if (b == nblocks - 1) { flags |= B3_CHUNK_END; blen = nbytes - 64u * b; }
+        b3_compress(cv, m, (u32)c, 0, blen, flags, o);
+        ACT_UNROLL for (int i = 0; i < 8; i++) cv[i] = o[i];
+    }
+    store8(cvs + ((size_t)ACT_SPEND_CHUNKS * p + c) * 8, cv);
+}
+// folds the CVs, derives the challenge, sets the final status of the verification
+ACT_FN void spend_finish_thread(const act_ctx* C, size_t p, const u32* proofs, u32* cvs, const u32* flags, u8* status) {
+    (void)C;
+    u32* cv = cvs + (size_t)ACT_SPEND_CHUNKS * p * 8;
+    u32 o[16], m[16];
+    // 16 chunks = perfect binary tree; fold in place level by level
+    ACT_NOUNROLL for (int width = ACT_SPEND_CHUNKS; width > 2; width >>= 1) {
+        ACT_NOUNROLL for (int k = 0; k < width / 2; k++) {
+            load8(m, cv + 16 * k); load8(m + 8, cv + 16 * k + 8);
+            b3_compress(B3_IV_, m, 0, 0, 64, B3_PARENT, o);
+            store8(cv + 8 * k, o);
+        }
+    }
+    load8(m, cv); load8(m + 8, cv + 8);
+    b3_compress(B3_IV_, m, 0, 0, 64, B3_PARENT | B3_ROOT, o);
+    sc g2 = sc_from_wide(o);
+    sc gamma = load_scalar(proofs + (size_t)ACT_PROOF_WORDS * p + 8 * 132);
+    u32 fl = flags[p];
+    u32 st = ACT_ST_OK;
+    if (fl & ACT_FLAG_BAD_POINT) st = ACT_ST_DECODE_INVALID_POINT;
+    else if (fl & ACT_FLAG_IDENTITY) st = ACT_ST_IDENTITY_POINT;
+    else if (!sc_eq(g2, gamma)) st = ACT_ST_INVALID_CLIENT_SPEND_PROOF;                    // (:842-844)
+    status[p] = (u8)st;
+}
+
+// =============================================================================================================
+// refund signing tail (src/lib.rs:846-868).  One thread per proof; rejected proofs get zero output.
+// refunds: n x 32 words (A*, e*, gamma, z); nullifiers: n x 8 words (reduced k).
+// =============================================================================================================
+ACT_FN void refund_sign_thread(const act_ctx* C, size_t p, const u32* proofs, const u32* rnd, const u32* kprime,
+                               const u8* status, u32* refunds, u32* nullifiers) {
+    u32* out = refunds + 32 * p;
+    if (status[p] != ACT_ST_OK) {
+        ACT_NOUNROLL for (int k = 0; k < 4; k++) store8_zero(out + 8 * k);
+        store8_zero(nullifiers + 8 * p);
+        return;
+    }
+    ge Kp;
+    const u32* kp = kprime + 32 * p;
+    load_fe(&Kp.X, kp); load_fe(&Kp.Y, kp + 8); load_fe(&Kp.Z, kp + 16); load_fe(&Kp.T, kp + 24);
+    ge X_A = ge_add(Kp, ge_basepoint());                                                   // (:848)
+    u32 r[32];
+    ACT_NOUNROLL for (int k = 0; k < 4; k++) load8(r + 8 * k, rnd + 32 * p + 8 * k);
+    u32 A_enc[8];
+    sc e, g, z, dummy = sc_zero();
+    bbs_sign_(C, &X_A, r, ACT_TR_REFUND, &dummy, A_enc, &e, &g, &z);
+    store8(out, A_enc); store_scalar(out + 8, e); store_scalar(out + 16, g); store_scalar(out + 24, z);
+    store_scalar(nullifiers + 8 * p, load_scalar(proofs + (size_t)ACT_PROOF_WORDS * p));   // nullifier() = k (:720-722)
+}
+
+// =============================================================================================================
+// PreRefund::to_credit_token verification (src/lib.rs:1217-1253).  com: n x 128 x 8 words, refund: n x 32 words.
+// =============================================================================================================
+ACT_FN void refund_check_thread(const act_ctx* C, size_t i, const u32* com, const u32* refund, u8* status) {
+    const u32* rf = refund + 32 * i;
+    u32 aw[8];
+    load8(aw, rf);
+    ge A;
+    u32 valid = ristretto_decode_(&A, aw);
+    sc e = load_scalar(rf + 8), gamma = load_scalar(rf + 16), z = load_scalar(rf + 24);
+    ge Kp = ge_identity();
+    ACT_NOUNROLL for (int j = ACT_L - 1; j >= 0; j--) {                                    // (:1224-1230) Horner
+        ge P;
+        valid &= load_point(&P, com + ((size_t)ACT_L * i + j) * 8);
+        Kp = ge_dbl(Kp, true);
+        Kp = ge_add_niels(Kp, ge_affine_to_niels(P.X, P.Y));
+    }
+    ge X_A = ge_add(Kp, ge_basepoint());
+    sc dummy = sc_zero();
+    u32 ok = dleq_check_(C, ACT_TR_REFUND, &dummy, &e, &gamma, &z, aw, &A, &X_A);          // (:1232-1243)
+    status[i] = (u8)(!valid ? ACT_ST_DECODE_INVALID_POINT : (ok ? ACT_ST_OK : ACT_ST_INVALID_REFUND_PROOF));
+}
+
+// =============================================================================================================
+// engine set-up: fixed-base tables and Params::new
+// =============================================================================================================
+// entry (win, k) of the radix-2^W table of B: k * 2^(W*win) * B as affine Niels (k = 0: identity)
+template <int W, int ENT>
+ACT_FN void build_table_thread(const ge* B, int win, ge_niels* tab) {
+    ge P = *B;
+    ACT_NOUNROLL for (int i = 0; i < W * win; i++) P = ge_dbl(P, true);
+    ge_cached Pc = ge_to_cached(P);
+    ge Q = P;
+    ge_niels* row = tab + (size_t)win * ENT;
+    row[0] = ge_niels_identity();
+    ACT_NOUNROLL for (int k = 1; k < ENT; k++) {
+        row[k] = ge_to_niels(Q);
+        Q = ge_add_cached(Q, Pc);
+    }
+}
+// Params::new (src/lib.rs:291-354).  dom: the "ACT-v1:..." separator as bytes (dlen <= 800).
+// out: 3 x 8 words = enc(H1), enc(H2), enc(H3).
+ACT_FN void params_derive_thread(const u8* dom, u32 dlen, u32* out) {
+    u32 buf[256];
+    u8* bb = reinterpret_cast<u8*>(buf);
+    u32 o[16], seed[8];
+    ACT_NOUNROLL for (int i = 0; i < 256; i++) buf[i] = 0;
+    ACT_NOUNROLL for (int i = 0; i < 8; i++) bb[i] = (i < 4) ? 0 : (u8)(dlen >> (8 * (7 - i)));
+    ACT_NOUNROLL for (u32 i = 0; i < dlen; i++) bb[8 + i] = dom[i];
+    b3_hash_single_chunk(buf, 8 + dlen, o);
+    ACT_UNROLL for (int i = 0; i < 8; i++) seed[i] = o[i];
+    ACT_NOUNROLL for (u32 ctr = 0; ctr < 3; ctr++) {
+        u32 n = 8 + dlen;
+        ACT_NOUNROLL for (int i = 0; i < 8; i++) bb[n + i] = (i == 7) ? 32 : 0;
+        n += 8;
+        ACT_NOUNROLL for (int i = 0; i < 32; i++) bb[n + i] = (u8)(seed[i >> 2] >> (8 * (i & 3)));
+        n += 32;
+        ACT_NOUNROLL for (int i = 0; i < 8; i++) bb[n + i] = (i == 7) ? 4 : 0;
+        n += 8;
+        bb[n] = (u8)ctr; bb[n + 1] = 0; bb[n + 2] = 0; bb[n + 3] = 0;
+        n += 4;
+        b3_hash_single_chunk(buf, n, o);
+        ge H = ristretto_from_uniform(o);
+        ristretto_encode_(out + 8 * ctr, &H);
+    }
+}

@@ -1,0 +1,503 @@
+// act_engine.cu -- CUDA kernels (sm_100a) and the C-ABI engine of include/act_engine.h.
+//
+// One engine = one (Params, PrivateKey) pair on one GPU: generator tables, the secret scalar, two
+// CUDA streams and the scratch buffers of the spend pipeline.  Batches are processed in chunks; the
+// host-buffer entry points double-buffer H2D / compute / D2H across the two streams.
+//
+// There is no CPU path: every entry point needs a CUDA device and fails otherwise.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/act_engine.h"
+#include "act_device.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// kernels: thin index wrappers around the per-thread bodies in act_device.cuh
+// ---------------------------------------------------------------------------------------------------
+#define ACT_ISSUE_BLOCK 128
+#define ACT_HEAD_BLOCK 64
+#define ACT_SIGN_BLOCK 64
+#define ACT_HASH_BLOCK 128
+
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK) issue_kernel(const act_ctx* C, size_t n, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) issue_thread(C, i, req, cs, rnd, resp, status);
+}
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK) issuance_check_kernel(const act_ctx* C, size_t n, const u32* K, const u32* resp, u8* status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) issuance_check_thread(C, i, K, resp, status);
+}
+// one block of 128 threads per proof: thread j owns com_j and the pair C'_j0, C'_j1
+__global__ void __launch_bounds__(ACT_L) spend_range_kernel(const act_ctx* C, const u32* proofs, u32* items, u32* com_niels, u32* flags) {
+    spend_range_thread(C, blockIdx.x, threadIdx.x, proofs, items, com_niels, flags);
+}
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) spend_head_thread(C, p, proofs, items, com_niels, kprime, flags);
+}
+__global__ void __launch_bounds__(ACT_HASH_BLOCK) spend_chunk_kernel(const act_ctx* C, size_t n, const u32* items, u32* cvs) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n * ACT_SPEND_CHUNKS) spend_chunk_thread(C, t / ACT_SPEND_CHUNKS, (int)(t % ACT_SPEND_CHUNKS), items, cvs);
+}
+__global__ void __launch_bounds__(ACT_HASH_BLOCK) spend_finish_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* cvs, const u32* flags, u8* status) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) spend_finish_thread(C, p, proofs, cvs, flags, status);
+}
+__global__ void __launch_bounds__(ACT_SIGN_BLOCK) refund_sign_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* rnd, const u32* kprime, const u8* status, u32* refunds, u32* nullifiers) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) refund_sign_thread(C, p, proofs, rnd, kprime, status, refunds, nullifiers);
+}
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK) refund_check_kernel(const act_ctx* C, size_t n, const u32* com, const u32* refund, u8* status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) refund_check_thread(C, i, com, refund, status);
+}
+
+// ---- set-up kernels ----
+__global__ void params_derive_kernel(const u8* dom, u32 dlen, u32* out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) params_derive_thread(dom, dlen, out);
+}
+// decodes H1,H2,H3,W into bases[1..3], W; bases[0] = G.  ok[0] = all valid
+__global__ void setup_decode_kernel(const u32* enc /* 4 x 8 words: H1,H2,H3,W */, ge* bases /* 4 */, ge* W, u32* ok) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        u32 v = 1;
+        bases[0] = ge_basepoint();
+        for (int i = 0; i < 3; i++) v &= ristretto_decode_(&bases[1 + i], enc + 8 * i);
+        v &= ristretto_decode_(W, enc + 24);
+        *ok = v;
+    }
+}
+// grid: 4 bases x 32 windows (vartime radix-256 tables), one thread each
+__global__ void build_fb_tables_kernel(const ge* bases, ge_niels* tabs) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 4 * ACT_FB_WIN) build_table_thread<8, ACT_FB_ENT>(&bases[t / ACT_FB_WIN], t % ACT_FB_WIN, tabs + (size_t)(t / ACT_FB_WIN) * ACT_FB_SIZE);
+}
+__global__ void build_ct_table_kernel(const ge* bases, ge_niels* tab) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ACT_CT_WIN) build_table_thread<4, ACT_CT_ENT>(&bases[0], t, tab);
+}
+// reduce the stored secret mod l once (Scalar::from_bytes_mod_order semantics for the key)
+__global__ void finalize_ctx_kernel(act_ctx* C) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) C->x = sc_from_words(C->x.v);
+}
+__global__ void public_key_kernel(const ge_niels* ct_g, const u32* x, u32* out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc s = sc_from_words(x);
+        ge W = fb_accumulate_ct(ge_identity(), ct_g, s);
+        ristretto_encode_(out, &W);
+    }
+}
+
+// ---- device self-test: PTX field arithmetic against the portable formulation, plus known answers ----
+__device__ void selftest_mul_portable(u32* r, const fe& a, const fe& b) {
+    for (int i = 0; i < 16; i++) r[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        u64 c = 0;
+        for (int j = 0; j < 8; j++) { c += (u64)a.v[j] * b.v[i] + r[i + j]; r[i + j] = (u32)c; c >>= 32; }
+        r[i + 8] = (u32)c;
+    }
+}
+__device__ u32 selftest_rng(u32& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+__global__ void selftest_kernel(u32* fail) {
+    u32 seed = 0x9e3779b9u * (blockIdx.x * blockDim.x + threadIdx.x + 1);
+    u32 bad = 0;
+    for (int it = 0; it < 64; it++) {
+        fe a, b;
+        for (int i = 0; i < 8; i++) { a.v[i] = selftest_rng(seed); b.v[i] = selftest_rng(seed); }
+        if (it % 8 == 1) for (int i = 0; i < 8; i++) a.v[i] = 0xffffffffu;
+        if (it % 8 == 2) for (int i = 0; i < 8; i++) b.v[i] = 0xffffffffu;
+        if (it % 8 == 3) for (int i = 1; i < 8; i++) a.v[i] = 0;
+        // mul: compare canonical(PTX product) with canonical(portable product reduced by the generic path)
+        u32 r[16], t[9];
+        selftest_mul_portable(r, a, b);
+        u64 c = 0;
+        for (int i = 0; i < 8; i++) { c += (u64)r[i] + (u64)r[8 + i] * 38u; t[i] = (u32)c; c >>= 32; }
+        u64 c2 = c * 38u;
+        fe ref;
+        for (int i = 0; i < 8; i++) { c2 += t[i]; ref.v[i] = (u32)c2; c2 >>= 32; }
+        ref.v[0] += (u32)c2 * 38u;  // cannot carry: value wrapped
+        fe got = fe_mul(a, b);
+        if (!fe_eq(got, ref)) bad |= 1;
+        // add / sub consistency with big-int emulation through canon: (a+b)-b == a, (a-b)+b == a
+        if (!fe_eq(fe_sub(fe_add(a, b), b), a)) bad |= 2;
+        if (!fe_eq(fe_add(fe_sub(a, b), b), a)) bad |= 4;
+        // a * a^-1 == 1 (skip zero)
+        if (!fe_is_zero(a)) { if (!fe_eq(fe_mul(a, fe_invert(a)), fe_one())) bad |= 8; }
+        if (!fe_eq(fe_sq(a), fe_mul(a, a))) bad |= 16;
+    }
+    // basepoint encodes to the RFC 9496 generator
+    {
+        const u32 gen[8] = {0x0aaef2e2u, 0x714ebc6au, 0x61a984a8u, 0x5f5100c5u, 0x6a0be358u, 0x8ddd82a5u, 0x4559a6b6u, 0x762d8de0u};
+        ge B = ge_basepoint();
+        u32 w[8];
+        ristretto_encode_(w, &B);
+        for (int i = 0; i < 8; i++) if (w[i] != gen[i]) bad |= 32;
+        ge D;
+        if (!ristretto_decode_(&D, gen)) bad |= 64;
+        ristretto_encode_(w, &D);
+        for (int i = 0; i < 8; i++) if (w[i] != gen[i]) bad |= 128;
+    }
+    if (bad) atomicOr(fail, bad);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char* what, cudaError_t e) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return -2;
+}
+static int fail_msg(const char* what) { g_err = what; return -1; }
+#define CK(call)                                       \
+    do {                                               \
+        cudaError_t e_ = (call);                       \
+        if (e_ != cudaSuccess) return fail(#call, e_); \
+    } while (0)
+
+#define ACT_SPEND_CHUNK 16384   // proofs per pipeline chunk
+#define ACT_SMALL_CHUNK 262144  // requests per chunk for the light-weight paths
+
+struct spend_scratch {
+    u32 *items = nullptr, *com_niels = nullptr, *kprime = nullptr, *flags = nullptr, *cvs = nullptr;
+    size_t cap = 0;
+};
+struct io_slot {  // device staging for the host-buffer entry points
+    u8 *in0 = nullptr, *in1 = nullptr, *in2 = nullptr, *out0 = nullptr, *out1 = nullptr, *st = nullptr;
+    size_t cap_in0 = 0, cap_in1 = 0, cap_in2 = 0, cap_out0 = 0, cap_out1 = 0, cap_st = 0;
+};
+
+struct act_engine {
+    int device = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    act_ctx* d_ctx = nullptr;
+    ge_niels* d_tables = nullptr;
+    ge* d_bases = nullptr;
+    spend_scratch scratch[2];
+    io_slot io[2];
+    uint64_t launches = 0;
+};
+
+static int ensure(u8** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CK(cudaMalloc((void**)p, need));
+    *cap = need;
+    return 0;
+}
+static int ensure_scratch(spend_scratch* s, size_t n) {
+    if (s->cap >= n) return 0;
+    cudaFree(s->items); cudaFree(s->com_niels); cudaFree(s->kprime); cudaFree(s->flags); cudaFree(s->cvs);
+    s->cap = 0;
+    CK(cudaMalloc((void**)&s->items, n * ACT_ITEM_WORDS * 4));
+    CK(cudaMalloc((void**)&s->com_niels, n * ACT_L * 96));
+    CK(cudaMalloc((void**)&s->kprime, n * 128));
+    CK(cudaMalloc((void**)&s->flags, n * 4));
+    CK(cudaMalloc((void**)&s->cvs, n * ACT_SPEND_CHUNKS * 32));
+    s->cap = n;
+    return 0;
+}
+
+extern "C" const char* act_last_error(void) { return g_err.c_str(); }
+extern "C" int act_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" void* act_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void act_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int act_params_derive(int device, const char* org, const char* svc, const char* dep, const char* ver, uint8_t h[96]) {
+    if (!org || !svc || !dep || !ver || !h) return fail_msg("act_params_derive: null argument");
+    std::string dom = std::string("ACT-v1:") + org + ":" + svc + ":" + dep + ":" + ver;  // src/lib.rs:293-296
+    if (dom.size() > 900) return fail_msg("act_params_derive: domain separator longer than 900 bytes");
+    CK(cudaSetDevice(device));
+    u8* d_dom = nullptr; u32* d_out = nullptr;
+    CK(cudaMalloc((void**)&d_dom, dom.size() + 1));
+    CK(cudaMalloc((void**)&d_out, 96));
+    CK(cudaMemcpy(d_dom, dom.data(), dom.size(), cudaMemcpyHostToDevice));
+    params_derive_kernel<<<1, 1>>>(d_dom, (u32)dom.size(), d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(h, d_out, 96, cudaMemcpyDeviceToHost));
+    cudaFree(d_dom); cudaFree(d_out);
+    return 0;
+}
+
+static void build_prefix(act_ctx* c, int which, const char* label, const uint8_t h[96]) {
+    // src/transcript.rs:54-74: u64be(43) | version | 3 x (u64be(32) | enc(H_i)) | u64be(len(label)) | label
+    static const char ver[] = "curve25519-ristretto anonymous-credits v1.0";
+    uint8_t buf[192];
+    memset(buf, 0, sizeof buf);
+    size_t n = 0;
+    buf[7] = 43; n = 8;
+    memcpy(buf + n, ver, 43); n += 43;
+    for (int i = 0; i < 3; i++) { buf[n + 7] = 32; n += 8; memcpy(buf + n, h + 32 * i, 32); n += 32; }
+    size_t ll = strlen(label);
+    buf[n + 7] = (uint8_t)ll; n += 8;
+    memcpy(buf + n, label, ll); n += ll;
+    memcpy(c->prefix[which], buf, 192);
+    c->prefix_len[which] = (u32)n;
+}
+
+extern "C" void act_engine_destroy(act_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    if (e->d_ctx) { cudaMemset(e->d_ctx, 0, sizeof(act_ctx)); cudaFree(e->d_ctx); }  // zeroise x on the device
+    cudaFree(e->d_tables); cudaFree(e->d_bases);
+    for (int s = 0; s < 2; s++) {
+        spend_scratch& sc_ = e->scratch[s];
+        cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs);
+        io_slot& io = e->io[s];
+        cudaFree(io.in0); cudaFree(io.in1); cudaFree(io.in2); cudaFree(io.out0); cudaFree(io.out1); cudaFree(io.st);
+        if (e->stream[s]) cudaStreamDestroy(e->stream[s]);
+    }
+    delete e;
+}
+
+extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[96], const uint8_t sk_x[32], const uint8_t pk_w[32]) {
+    if (!out || !h || !sk_x || !pk_w) return fail_msg("act_engine_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return fail_msg("act_engine_create: no CUDA device (this engine has no CPU path)");
+    if (device < 0 || device >= ndev) return fail_msg("act_engine_create: bad device index");
+    CK(cudaSetDevice(device));
+    act_engine* e = new act_engine();
+    e->device = device;
+    int rc = 0;
+    u32 *d_enc = nullptr, *d_ok = nullptr;
+    ge* d_W = nullptr;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaStreamCreateWithFlags(&e->stream[0], cudaStreamNonBlocking));
+        CKB(cudaStreamCreateWithFlags(&e->stream[1], cudaStreamNonBlocking));
+        CKB(cudaMalloc((void**)&e->d_ctx, sizeof(act_ctx)));
+        CKB(cudaMalloc((void**)&e->d_tables, sizeof(ge_niels) * (4 * (size_t)ACT_FB_SIZE + ACT_CT_SIZE)));
+        CKB(cudaMalloc((void**)&e->d_bases, sizeof(ge) * 4));
+        CKB(cudaMalloc((void**)&d_enc, 128));
+        CKB(cudaMalloc((void**)&d_ok, 4));
+        CKB(cudaMalloc((void**)&d_W, sizeof(ge)));
+        CKB(cudaMemcpy(d_enc, h, 96, cudaMemcpyHostToDevice));
+        CKB(cudaMemcpy(d_enc + 24, pk_w, 32, cudaMemcpyHostToDevice));
+        setup_decode_kernel<<<1, 1>>>(d_enc, e->d_bases, d_W, d_ok);
+        build_fb_tables_kernel<<<4, ACT_FB_WIN>>>(e->d_bases, e->d_tables);
+        build_ct_table_kernel<<<1, ACT_CT_WIN>>>(e->d_bases, e->d_tables + 4 * (size_t)ACT_FB_SIZE);
+        CKB(cudaGetLastError());
+        u32 ok = 0;
+        CKB(cudaMemcpy(&ok, d_ok, 4, cudaMemcpyDeviceToHost));
+        if (!ok) { rc = fail_msg("act_engine_create: H1/H2/H3/W is not a valid ristretto255 encoding"); break; }
+        // context
+        act_ctx hc;
+        memset(&hc, 0, sizeof hc);
+        for (int b = 0; b < 4; b++) hc.fb[b] = e->d_tables + (size_t)b * ACT_FB_SIZE;
+        hc.ct_g = e->d_tables + 4 * (size_t)ACT_FB_SIZE;
+        memcpy(hc.h_enc, h, 96);
+        build_prefix(&hc, ACT_TR_REQUEST, "request", h);
+        build_prefix(&hc, ACT_TR_RESPOND, "respond", h);
+        build_prefix(&hc, ACT_TR_REFUND, "refund", h);
+        build_prefix(&hc, ACT_TR_SPEND, "spend", h);
+        CKB(cudaMemcpy(&hc.W, d_W, sizeof(ge), cudaMemcpyDeviceToHost));
+        // raw key words; finalize_ctx_kernel reduces them mod l on the device
+        memcpy(hc.x.v, sk_x, 32);
+        CKB(cudaMemcpy(e->d_ctx, &hc, sizeof hc, cudaMemcpyHostToDevice));
+        memset(&hc, 0, sizeof hc);
+        finalize_ctx_kernel<<<1, 1>>>(e->d_ctx);
+        CKB(cudaGetLastError());
+        CKB(cudaDeviceSynchronize());
+#undef CKB
+    } while (0);
+    cudaFree(d_enc); cudaFree(d_ok); cudaFree(d_W);
+    if (rc) { act_engine_destroy(e); return rc; }
+    e->launches += 3;
+    *out = e;
+    return 0;
+}
+extern "C" int act_engine_device(const act_engine* e) { return e ? e->device : -1; }
+extern "C" uint64_t act_engine_launch_count(const act_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int act_public_key(int device, const uint8_t sk_x[32], uint8_t pk_w[32]) {
+    if (!sk_x || !pk_w) return fail_msg("act_public_key: null argument");
+    CK(cudaSetDevice(device));
+    ge* d_b = nullptr; ge_niels* d_t = nullptr; u32 *d_x = nullptr, *d_o = nullptr;
+    CK(cudaMalloc((void**)&d_b, sizeof(ge) * 4));
+    CK(cudaMalloc((void**)&d_t, sizeof(ge_niels) * ACT_CT_SIZE));
+    CK(cudaMalloc((void**)&d_x, 32)); CK(cudaMalloc((void**)&d_o, 32));
+    ge hb[4];
+    memset(hb, 0, sizeof hb);
+    CK(cudaMemcpy(d_x, sk_x, 32, cudaMemcpyHostToDevice));
+    u32 *d_enc = nullptr, *d_ok = nullptr; ge* d_W = nullptr;
+    // bases[0] = G via the set-up kernel with dummy (identity) encodings
+    CK(cudaMalloc((void**)&d_enc, 128)); CK(cudaMemset(d_enc, 0, 128));
+    CK(cudaMalloc((void**)&d_ok, 4)); CK(cudaMalloc((void**)&d_W, sizeof(ge)));
+    setup_decode_kernel<<<1, 1>>>(d_enc, d_b, d_W, d_ok);
+    build_ct_table_kernel<<<1, ACT_CT_WIN>>>(d_b, d_t);
+    public_key_kernel<<<1, 1>>>(d_t, d_x, d_o);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(pk_w, d_o, 32, cudaMemcpyDeviceToHost));
+    cudaMemset(d_x, 0, 32);
+    cudaFree(d_b); cudaFree(d_t); cudaFree(d_x); cudaFree(d_o); cudaFree(d_enc); cudaFree(d_ok); cudaFree(d_W);
+    return 0;
+}
+
+extern "C" int act_selftest(int device) {
+    CK(cudaSetDevice(device));
+    u32* d_fail = nullptr;
+    CK(cudaMalloc((void**)&d_fail, 4));
+    CK(cudaMemset(d_fail, 0, 4));
+    selftest_kernel<<<8, 64>>>(d_fail);
+    CK(cudaGetLastError());
+    u32 f = 0;
+    CK(cudaMemcpy(&f, d_fail, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_fail);
+    if (f) { char b[64]; snprintf(b, sizeof b, "act_selftest: failure mask 0x%x", f); g_err = b; return (int)f; }
+    return 0;
+}
+
+static inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- device-buffer entry points ----
+extern "C" int act_batch_issue_dev(act_engine* e, size_t n, const void* req, const void* c, const void* rnd, void* resp, void* status, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    issue_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)req, (const u32*)c, (const u32*)rnd, (u32*)resp, (u8*)status);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int act_batch_issuance_check_dev(act_engine* e, size_t n, const void* K, const void* resp, void* status, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    issuance_check_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)K, (const u32*)resp, (u8*)status);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* com, const void* refund, void* status, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    refund_check_kernel<<<nblocks(n, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)com, (const u32*)refund, (u8*)status);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+// one chunk of the spend pipeline on one stream with one scratch set
+static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, size_t m, const u32* proofs, const u32* rnd,
+                              u32* refunds, u32* nullifiers, u8* status) {
+    CK(cudaMemsetAsync(s->flags, 0, m * 4, st));
+    spend_range_kernel<<<(unsigned)m, ACT_L, 0, st>>>(e->d_ctx, proofs, s->items, s->com_niels, s->flags);
+    spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->kprime, s->flags);
+    spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, s->items, s->cvs);
+    spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status);
+    refund_sign_kernel<<<nblocks(m, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, m, proofs, rnd, s->kprime, status, refunds, nullifiers);
+    e->launches += 5;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int act_batch_verify_spend_and_refund_dev(act_engine* e, size_t n, const void* proofs, const void* rnd, void* refunds,
+                                                      void* nullifiers, void* status, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    size_t cap = n < ACT_SPEND_CHUNK ? n : ACT_SPEND_CHUNK;
+    int rc = ensure_scratch(&e->scratch[0], cap);
+    if (rc) return rc;
+    for (size_t off = 0; off < n; off += ACT_SPEND_CHUNK) {
+        size_t m = n - off < ACT_SPEND_CHUNK ? n - off : ACT_SPEND_CHUNK;
+        rc = spend_chunk_launch(e, &e->scratch[0], st, m, (const u32*)proofs + off * ACT_PROOF_WORDS, (const u32*)rnd + off * 32,
+                                (u32*)refunds + off * 32, (u32*)nullifiers + off * 8, (u8*)status + off);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---- host-buffer entry points: chunked, double-buffered over the engine's two streams ----
+struct host_io {
+    const uint8_t* in[3]; size_t in_stride[3];
+    uint8_t* out[3]; size_t out_stride[3];  // out[2] = status (stride 1)
+};
+template <typename F>
+static int run_chunked(act_engine* e, size_t n, size_t chunk, const host_io& h, F launch) {
+    CK(cudaSetDevice(e->device));
+    size_t nchunks = (n + chunk - 1) / chunk;
+    for (size_t ci = 0; ci < nchunks; ci++) {
+        int s = (int)(ci & 1);
+        io_slot& io = e->io[s];
+        cudaStream_t st = e->stream[s];
+        size_t off = ci * chunk, m = n - off < chunk ? n - off : chunk;
+        CK(cudaStreamSynchronize(st));  // slot reuse: previous chunk on this slot fully drained (incl. D2H)
+        int rc;
+        if ((rc = ensure(&io.in0, &io.cap_in0, m * h.in_stride[0] + 16))) return rc;
+        if (h.in[1] && (rc = ensure(&io.in1, &io.cap_in1, m * h.in_stride[1] + 16))) return rc;
+        if (h.in[2] && (rc = ensure(&io.in2, &io.cap_in2, m * h.in_stride[2] + 16))) return rc;
+        if (h.out[0] && (rc = ensure(&io.out0, &io.cap_out0, m * h.out_stride[0] + 16))) return rc;
+        if (h.out[1] && (rc = ensure(&io.out1, &io.cap_out1, m * h.out_stride[1] + 16))) return rc;
+        if ((rc = ensure(&io.st, &io.cap_st, m + 16))) return rc;
+        CK(cudaMemcpyAsync(io.in0, h.in[0] + off * h.in_stride[0], m * h.in_stride[0], cudaMemcpyHostToDevice, st));
+        if (h.in[1]) CK(cudaMemcpyAsync(io.in1, h.in[1] + off * h.in_stride[1], m * h.in_stride[1], cudaMemcpyHostToDevice, st));
+        if (h.in[2]) CK(cudaMemcpyAsync(io.in2, h.in[2] + off * h.in_stride[2], m * h.in_stride[2], cudaMemcpyHostToDevice, st));
+        if ((rc = launch(s, st, m, io))) return rc;
+        if (h.out[0]) CK(cudaMemcpyAsync(h.out[0] + off * h.out_stride[0], io.out0, m * h.out_stride[0], cudaMemcpyDeviceToHost, st));
+        if (h.out[1]) CK(cudaMemcpyAsync(h.out[1] + off * h.out_stride[1], io.out1, m * h.out_stride[1], cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h.out[2] + off, io.st, m, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(e->stream[0]));
+    CK(cudaStreamSynchronize(e->stream[1]));
+    return 0;
+}
+
+extern "C" int act_batch_issue(act_engine* e, size_t n, const uint8_t* req, const uint8_t* c, const uint8_t* rnd, uint8_t* resp, uint8_t* status) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!req || !c || !rnd || !resp || !status) return fail_msg("act_batch_issue: null buffer");
+    host_io h = {{req, c, rnd}, {128, 32, 128}, {resp, nullptr, status}, {160, 0, 1}};
+    return run_chunked(e, n, ACT_SMALL_CHUNK, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
+        return act_batch_issue_dev(e, m, io.in0, io.in1, io.in2, io.out0, io.st, st);
+    });
+}
+extern "C" int act_batch_issuance_check(act_engine* e, size_t n, const uint8_t* K, const uint8_t* resp, uint8_t* status) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!K || !resp || !status) return fail_msg("act_batch_issuance_check: null buffer");
+    host_io h = {{K, resp, nullptr}, {32, 160, 0}, {nullptr, nullptr, status}, {0, 0, 1}};
+    return run_chunked(e, n, ACT_SMALL_CHUNK, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
+        return act_batch_issuance_check_dev(e, m, io.in0, io.in1, io.st, st);
+    });
+}
+extern "C" int act_batch_refund_check(act_engine* e, size_t n, const uint8_t* com, const uint8_t* refund, uint8_t* status) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!com || !refund || !status) return fail_msg("act_batch_refund_check: null buffer");
+    host_io h = {{com, refund, nullptr}, {4096, 128, 0}, {nullptr, nullptr, status}, {0, 0, 1}};
+    return run_chunked(e, n, ACT_SPEND_CHUNK, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
+        return act_batch_refund_check_dev(e, m, io.in0, io.in1, io.st, st);
+    });
+}
+extern "C" int act_batch_verify_spend_and_refund(act_engine* e, size_t n, const uint8_t* proofs, const uint8_t* rnd, uint8_t* refunds,
+                                                  uint8_t* nullifiers, uint8_t* status) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!proofs || !rnd || !refunds || !nullifiers || !status) return fail_msg("act_batch_verify_spend_and_refund: null buffer");
+    host_io h = {{proofs, rnd, nullptr}, {ACT_PROOF_BYTES, 128, 0}, {refunds, nullifiers, status}, {128, 32, 1}};
+    return run_chunked(e, n, ACT_SPEND_CHUNK, h, [&](int s, cudaStream_t st, size_t m, io_slot& io) {
+        int rc = ensure_scratch(&e->scratch[s], m < ACT_SPEND_CHUNK ? m : ACT_SPEND_CHUNK);
+        if (rc) return rc;
+        return spend_chunk_launch(e, &e->scratch[s], st, m, (const u32*)io.in0, (const u32*)io.in1, (u32*)io.out0, (u32*)io.out1, io.st);
+    });
+}

@@ -1,0 +1,378 @@
+// fe25519.cuh -- GF(2^255-19) on 8 saturated 32-bit limbs (radix 2^32) for sm_100a.
+//
+// Values are kept "loosely reduced": any representative in [0, 2^256).  2^256 = 38 (mod p), so a
+// 512-bit product folds as lo + 38*hi.  The 8x8 limb product runs on the integer multiply pipe as
+// IMAD.WIDE.U32(.X) chains: mad.lo.cc/madc.hi.cc pairs of one (a_j, b_i) fuse into a single
+// 32x32+64 -> 64 multiply-add with carry-in/out predicates (checked with cuobjdump -sass), and the
+// even/odd column split keeps every chain free of overlapping 64-bit slots.
+//
+// Replaces curve25519-dalek's FieldElement (un-vendored dependency of /root/reference, Cargo.lock:267):
+// used by every point operation behind src/lib.rs:621-663 and :781-869.
+//
+// The same source compiles for the host (plain C++ paths, no PTX) ONLY for tests/hostsim, which
+// unit-tests the arithmetic logic without a GPU; the product library never uses the host path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ACT_FN __device__ __forceinline__
+#define ACT_NOINLINE __device__ __noinline__
+#define ACT_CONST __device__ __constant__ const
+#else
+#define ACT_FN static inline
+#define ACT_NOINLINE static
+#define ACT_CONST static const
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define ACT_PTX 1
+#define ACT_UNROLL _Pragma("unroll")
+#define ACT_NOUNROLL _Pragma("unroll 1")
+#else
+#define ACT_PTX 0
+#define ACT_UNROLL
+#define ACT_NOUNROLL
+#endif
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint8_t u8;
+
+struct fe { u32 v[8]; };
+
+ACT_CONST u32 FE_D_[8] = {0x135978a3u, 0x75eb4dcau, 0x4141d8abu, 0x00700a4du, 0x7779e898u, 0x8cc74079u, 0x2b6ffe73u, 0x52036ceeu};
+ACT_CONST u32 FE_D2_[8] = {0x26b2f159u, 0xebd69b94u, 0x8283b156u, 0x00e0149au, 0xeef3d130u, 0x198e80f2u, 0x56dffce7u, 0x2406d9dcu};
+ACT_CONST u32 FE_SQRT_M1_[8] = {0x4a0ea0b0u, 0xc4ee1b27u, 0xad2fe478u, 0x2f431806u, 0x3dfbd7a7u, 0x2b4d0099u, 0x4fc1df0bu, 0x2b832480u};
+ACT_CONST u32 FE_SQRT_AD_MINUS_ONE_[8] = {0x497b2e1bu, 0x7e97f6a0u, 0x1b7854bdu, 0xaf9d8e0cu, 0x31f5d1fdu, 0x0f3cfcc9u, 0x2b8348acu, 0x376931bfu};
+ACT_CONST u32 FE_INVSQRT_A_MINUS_D_[8] = {0x805d40eau, 0x99c8fdaau, 0x5a4172beu, 0x9d2f1617u, 0xfe01d840u, 0x16c27b91u, 0xcfaffca2u, 0x786c8905u};
+ACT_CONST u32 FE_ONE_MINUS_D_SQ_[8] = {0x945fc176u, 0xe27c09c1u, 0xcd5e350fu, 0x2c81a138u, 0xbe70dfe4u, 0x9994abddu, 0xb2b3e0d7u, 0x029072a8u};
+ACT_CONST u32 FE_D_MINUS_ONE_SQ_[8] = {0x44ed4d20u, 0x31ad5aaau, 0xb01e1999u, 0xd29e4a2cu, 0x529b4eebu, 0x4cdcd32fu, 0xf66c2241u, 0x5968b37au};
+ACT_CONST u32 FE_BX_[8] = {0x8f25d51au, 0xc9562d60u, 0x9525a7b2u, 0x692cc760u, 0xfdd6dc5cu, 0xc0a4e231u, 0xcd6e53feu, 0x216936d3u};
+ACT_CONST u32 FE_BY_[8] = {0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u};
+ACT_CONST u32 FE_BT_[8] = {0xa5b7dda3u, 0x6dde8ab3u, 0x775152f5u, 0x20f09f80u, 0x64abe37du, 0x66ea4e8eu, 0xd78b7665u, 0x67875f0fu};
+
+ACT_FN fe fe_const(const u32* c) {
+    fe r;
+    ACT_UNROLL for (int i = 0; i < 8; i++) r.v[i] = c[i];
+    return r;
+}
+#define FE_D fe_const(FE_D_)
+#define FE_D2 fe_const(FE_D2_)
+#define FE_SQRT_M1 fe_const(FE_SQRT_M1_)
+#define FE_SQRT_AD_MINUS_ONE fe_const(FE_SQRT_AD_MINUS_ONE_)
+#define FE_INVSQRT_A_MINUS_D fe_const(FE_INVSQRT_A_MINUS_D_)
+#define FE_ONE_MINUS_D_SQ fe_const(FE_ONE_MINUS_D_SQ_)
+#define FE_D_MINUS_ONE_SQ fe_const(FE_D_MINUS_ONE_SQ_)
+
+ACT_FN fe fe_zero() {
+    fe r;
+    ACT_UNROLL for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+}
+ACT_FN fe fe_one() { fe r = fe_zero(); r.v[0] = 1; return r; }
+
+// ---- add / sub -------------------------------------------------------------------------------
+// r = a + b (mod p), loosely reduced.  Carry out of 2^256 folds back as +38 (twice: the second fold
+// cannot propagate because the wrapped value is then < 2^13).
+ACT_FN fe fe_add(const fe& a, const fe& b) {
+    fe r;
+#if ACT_PTX
+    u32 c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    u32 f = c * 38u;
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.cc.u32 %7, %7, 0;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c)
+        : "r"(f));
+    r.v[0] += c * 38u;
+#else
+    u64 c = 0;
+    for (int i = 0; i < 8; i++) { c += (u64)a.v[i] + b.v[i]; r.v[i] = (u32)c; c >>= 32; }
+    c *= 38;
+    for (int i = 0; i < 8; i++) { c += r.v[i]; r.v[i] = (u32)c; c >>= 32; }
+    r.v[0] += (u32)c * 38u;
+#endif
+    return r;
+}
+
+// r = a - b (mod p).  A borrow out of 2^256 folds back as -38 (twice, same argument as fe_add).
+ACT_FN fe fe_sub(const fe& a, const fe& b) {
+    fe r;
+#if ACT_PTX
+    u32 c;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    u32 f = c & 38u;  // c is 0 or 0xffffffff
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t"
+        "subc.cc.u32 %5, %5, 0;\n\t"
+        "subc.cc.u32 %6, %6, 0;\n\t"
+        "subc.cc.u32 %7, %7, 0;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c)
+        : "r"(f));
+    r.v[0] -= c & 38u;
+#else
+    int64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (int64_t)a.v[i] - b.v[i]; r.v[i] = (u32)c; c >>= 32; }
+    int64_t f = c ? 38 : 0;
+    c = -f;
+    for (int i = 0; i < 8; i++) { c += (int64_t)r.v[i]; r.v[i] = (u32)c; c >>= 32; }
+    if (c) r.v[0] -= 38u;
+#endif
+    return r;
+}
+ACT_FN fe fe_neg(const fe& a) { return fe_sub(fe_zero(), a); }
+
+// ---- 8x8 -> 16 limb product ------------------------------------------------------------------
+#if ACT_PTX
+// acc[0..7] += {a0,a1,a2,a3} * bi placed in non-overlapping 64-bit slots, carry into acc[8]
+ACT_FN void fe_row_chain(u32* acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bi));
+}
+#endif
+
+// t[0..8] (value < 39 * 2^256) -> loosely reduced fe
+ACT_FN fe fe_fold9(u32* t) {
+    fe r;
+#if ACT_PTX
+    u32 f = t[8] * 38u, c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, 0;\n\t"
+        "addc.cc.u32 %2, %11, 0;\n\t"
+        "addc.cc.u32 %3, %12, 0;\n\t"
+        "addc.cc.u32 %4, %13, 0;\n\t"
+        "addc.cc.u32 %5, %14, 0;\n\t"
+        "addc.cc.u32 %6, %15, 0;\n\t"
+        "addc.cc.u32 %7, %16, 0;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c)
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(f));
+    r.v[0] += c * 38u;
+#else
+    u64 c = (u64)t[8] * 38u;
+    for (int i = 0; i < 8; i++) { c += t[i]; r.v[i] = (u32)c; c >>= 32; }
+    r.v[0] += (u32)c * 38u;
+#endif
+    return r;
+}
+
+// 512-bit r[0..15] -> fe : lo + 38*hi
+ACT_FN fe fe_reduce512(const u32* r) {
+    u32 t[9];
+#if ACT_PTX
+    const u32 k38 = 38u;
+    ACT_UNROLL for (int i = 0; i < 8; i++) t[i] = r[i];
+    t[8] = 0;
+    // even hi limbs into slots (0,1)(2,3)(4,5)(6,7); odd hi limbs into (1,2)(3,4)(5,6)(7,8)
+    fe_row_chain(t, r[8], r[10], r[12], r[14], k38);
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+        : "r"(r[9]), "r"(r[11]), "r"(r[13]), "r"(r[15]), "r"(k38));
+#else
+    u64 c = 0;
+    for (int i = 0; i < 8; i++) { c += (u64)r[i] + (u64)r[8 + i] * 38u; t[i] = (u32)c; c >>= 32; }
+    t[8] = (u32)c;
+#endif
+    return fe_fold9(t);
+}
+
+ACT_FN fe fe_mul(const fe& a, const fe& b) {
+    u32 r[16];
+#if ACT_PTX
+    u32 ev[18], od[18];
+    ACT_UNROLL for (int i = 0; i < 18; i++) { ev[i] = 0; od[i] = 0; }
+    ACT_UNROLL for (int i = 0; i < 8; i += 2) {
+        fe_row_chain(ev + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+        fe_row_chain(od + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+        fe_row_chain(od + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
+        fe_row_chain(ev + i + 2, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+    }
+    // r = ev + (od << 32), one 15-word carry chain in a single asm statement (30 operands)
+    ACT_UNROLL for (int i = 0; i < 16; i++) r[i] = ev[i];
+    asm("add.cc.u32 %0, %0, %15;\n\t"
+        "addc.cc.u32 %1, %1, %16;\n\t"
+        "addc.cc.u32 %2, %2, %17;\n\t"
+        "addc.cc.u32 %3, %3, %18;\n\t"
+        "addc.cc.u32 %4, %4, %19;\n\t"
+        "addc.cc.u32 %5, %5, %20;\n\t"
+        "addc.cc.u32 %6, %6, %21;\n\t"
+        "addc.cc.u32 %7, %7, %22;\n\t"
+        "addc.cc.u32 %8, %8, %23;\n\t"
+        "addc.cc.u32 %9, %9, %24;\n\t"
+        "addc.cc.u32 %10, %10, %25;\n\t"
+        "addc.cc.u32 %11, %11, %26;\n\t"
+        "addc.cc.u32 %12, %12, %27;\n\t"
+        "addc.cc.u32 %13, %13, %28;\n\t"
+        "addc.u32 %14, %14, %29;"
+        : "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+          "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]),
+          "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+#else
+    for (int i = 0; i < 16; i++) r[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        u64 c = 0;
+        for (int j = 0; j < 8; j++) { c += (u64)a.v[j] * b.v[i] + r[i + j]; r[i + j] = (u32)c; c >>= 32; }
+        r[i + 8] = (u32)c;
+    }
+#endif
+    return fe_reduce512(r);
+}
+
+ACT_FN fe fe_sq(const fe& a) { return fe_mul(a, a); }
+
+ACT_FN fe fe_sqn(fe a, int n) {
+    ACT_NOUNROLL for (int i = 0; i < n; i++) a = fe_sq(a);
+    return a;
+}
+
+// ---- canonical form, predicates ----------------------------------------------------------------
+// fully reduced representative in [0, p)
+ACT_FN fe fe_canon(const fe& a) {
+    fe r = a;
+    // fold bit 255: x = (x mod 2^255) + 19*(x >> 255)  -> < 2^255 + 19
+    u32 top = r.v[7] >> 31;
+    r.v[7] &= 0x7fffffffu;
+    u64 c = (u64)top * 19u;
+    ACT_UNROLL for (int i = 0; i < 8; i++) { c += r.v[i]; r.v[i] = (u32)c; c >>= 32; }
+    // if x >= p then x - p = (x + 19) mod 2^255
+    fe t;
+    c = 19;
+    ACT_UNROLL for (int i = 0; i < 8; i++) { c += r.v[i]; t.v[i] = (u32)c; c >>= 32; }
+    u32 ge = t.v[7] >> 31;  // bit 255 of x+19 set <=> x >= p
+    t.v[7] &= 0x7fffffffu;
+    u32 m = 0u - ge;
+    ACT_UNROLL for (int i = 0; i < 8; i++) r.v[i] = (r.v[i] & ~m) | (t.v[i] & m);
+    return r;
+}
+ACT_FN u32 fe_is_negative(const fe& a) { return fe_canon(a).v[0] & 1u; }
+ACT_FN u32 fe_is_zero(const fe& a) {
+    fe c = fe_canon(a);
+    u32 o = 0;
+    ACT_UNROLL for (int i = 0; i < 8; i++) o |= c.v[i];
+    return o == 0;
+}
+ACT_FN u32 fe_eq(const fe& a, const fe& b) { return fe_is_zero(fe_sub(a, b)); }
+// r = b ? y : x   (branch-free)
+ACT_FN fe fe_select(const fe& x, const fe& y, u32 b) {
+    fe r;
+    u32 m = 0u - (b & 1u);
+    ACT_UNROLL for (int i = 0; i < 8; i++) r.v[i] = (x.v[i] & ~m) | (y.v[i] & m);
+    return r;
+}
+ACT_FN fe fe_cneg(const fe& x, u32 b) { return fe_select(x, fe_neg(x), b); }
+ACT_FN fe fe_abs(const fe& x) { return fe_cneg(x, fe_is_negative(x)); }
+
+// ---- bytes -------------------------------------------------------------------------------------
+// little-endian words in, bit 255 ignored (dalek FieldElement::from_bytes)
+ACT_FN fe fe_from_words(const u32* w) {
+    fe r;
+    ACT_UNROLL for (int i = 0; i < 8; i++) r.v[i] = w[i];
+    r.v[7] &= 0x7fffffffu;
+    return r;
+}
+ACT_FN void fe_to_words(u32* w, const fe& a) {
+    fe c = fe_canon(a);
+    ACT_UNROLL for (int i = 0; i < 8; i++) w[i] = c.v[i];
+}
+
+// ---- exponentiations -----------------------------------------------------------------------------
+// z^(2^250-1), z^11
+ACT_NOINLINE void fe_pow22501(fe* t250, fe* z11, const fe* zp) {
+    fe z = *zp;
+    fe t0 = fe_sq(z);
+    fe t1 = fe_sqn(t0, 2);
+    t1 = fe_mul(z, t1);
+    t0 = fe_mul(t0, t1);
+    fe t2 = fe_sq(t0);
+    t1 = fe_mul(t1, t2);
+    t2 = fe_sqn(t1, 5); t1 = fe_mul(t2, t1);
+    t2 = fe_sqn(t1, 10); t2 = fe_mul(t2, t1);
+    fe t3 = fe_sqn(t2, 20); t2 = fe_mul(t3, t2);
+    t2 = fe_sqn(t2, 10); t1 = fe_mul(t2, t1);
+    t2 = fe_sqn(t1, 50); t2 = fe_mul(t2, t1);
+    t3 = fe_sqn(t2, 100); t2 = fe_mul(t3, t2);
+    t2 = fe_sqn(t2, 50); t1 = fe_mul(t2, t1);
+    *t250 = t1; *z11 = t0;
+}
+ACT_FN fe fe_invert(const fe& z) {
+    fe t, z11;
+    fe_pow22501(&t, &z11, &z);
+    t = fe_sqn(t, 5);
+    return fe_mul(t, z11);
+}
+ACT_FN fe fe_pow22523(const fe& z) {
+    fe t, z11;
+    fe_pow22501(&t, &z11, &z);
+    t = fe_sqn(t, 2);
+    return fe_mul(t, z);
+}
+
+// RFC 9496 4.2 SQRT_RATIO_M1 / dalek FieldElement::sqrt_ratio_i.  *was_square out, returns r >= 0.
+ACT_FN fe fe_sqrt_ratio_i(u32* was_square, const fe& u, const fe& v) {
+    fe v3 = fe_mul(fe_sq(v), v);
+    fe v7 = fe_mul(fe_sq(v3), v);
+    fe r = fe_mul(fe_mul(u, v3), fe_pow22523(fe_mul(u, v7)));
+    fe check = fe_mul(v, fe_sq(r));
+    fe neg_u = fe_neg(u);
+    fe neg_u_i = fe_mul(neg_u, FE_SQRT_M1);
+    u32 correct = fe_eq(check, u);
+    u32 flipped = fe_eq(check, neg_u);
+    u32 flipped_i = fe_eq(check, neg_u_i);
+    fe r_prime = fe_mul(FE_SQRT_M1, r);
+    r = fe_select(r, r_prime, flipped | flipped_i);
+    r = fe_abs(r);
+    *was_square = correct | flipped;
+    return r;
+}
+// 1/sqrt(v) when v is a nonzero square (dalek invsqrt = sqrt_ratio_i(1, v))
+ACT_FN fe fe_invsqrt(u32* was_square, const fe& v) { return fe_sqrt_ratio_i(was_square, fe_one(), v); }

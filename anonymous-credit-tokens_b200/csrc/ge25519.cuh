@@ -1,0 +1,172 @@
+// ge25519.cuh -- twisted Edwards (a = -1) point arithmetic in extended coordinates and the
+// ristretto255 encode / decode / one-way map (RFC 9496 4.3.1, 4.3.2, 4.3.4).
+//
+// Replaces curve25519-dalek's RistrettoPoint / CompressedRistretto as used by the reference at
+// src/lib.rs:629-651, 787-854 (point +, -, *), src/transcript.rs:106 (compress) and
+// src/cbor.rs:68-71 (decompress, with all rejection conditions).
+#pragma once
+#include "fe25519.cuh"
+#include "sc25519.cuh"
+
+struct ge { fe X, Y, Z, T; };             // extended: x = X/Z, y = Y/Z, xy = T/Z
+struct ge_cached { fe YpX, YmX, Z, T2d; };  // "projective Niels"
+struct ge_niels { fe ypx, ymx, xy2d; };     // affine Niels (Z = 1)
+
+ACT_FN ge ge_identity() { ge r; r.X = fe_zero(); r.Y = fe_one(); r.Z = fe_one(); r.T = fe_zero(); return r; }
+ACT_FN ge ge_basepoint() { ge r; r.X = fe_const(FE_BX_); r.Y = fe_const(FE_BY_); r.Z = fe_one(); r.T = fe_const(FE_BT_); return r; }
+ACT_FN ge_cached ge_cached_identity() { ge_cached r; r.YpX = fe_one(); r.YmX = fe_one(); r.Z = fe_one(); r.T2d = fe_zero(); return r; }
+ACT_FN ge_niels ge_niels_identity() { ge_niels r; r.ypx = fe_one(); r.ymx = fe_one(); r.xy2d = fe_zero(); return r; }
+
+ACT_FN ge_cached ge_to_cached(const ge& p) {
+    ge_cached r;
+    r.YpX = fe_add(p.Y, p.X); r.YmX = fe_sub(p.Y, p.X); r.Z = p.Z; r.T2d = fe_mul(p.T, FE_D2);
+    return r;
+}
+ACT_FN ge ge_neg(const ge& p) { ge r; r.X = fe_neg(p.X); r.Y = p.Y; r.Z = p.Z; r.T = fe_neg(p.T); return r; }
+
+// r = p + q, 8M (+1M for T when want_t)
+ACT_FN ge ge_add_cached(const ge& p, const ge_cached& q) {
+    fe PP = fe_mul(fe_add(p.Y, p.X), q.YpX);
+    fe MM = fe_mul(fe_sub(p.Y, p.X), q.YmX);
+    fe TT = fe_mul(p.T, q.T2d);
+    fe ZZ = fe_mul(p.Z, q.Z);
+    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe E = fe_sub(PP, MM), H = fe_add(PP, MM), G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
+    ge r;
+    r.X = fe_mul(E, F); r.Y = fe_mul(H, G); r.Z = fe_mul(G, F); r.T = fe_mul(E, H);
+    return r;
+}
+// r = p + q for affine-Niels q, 7M
+ACT_FN ge ge_add_niels(const ge& p, const ge_niels& q) {
+    fe PP = fe_mul(fe_add(p.Y, p.X), q.ypx);
+    fe MM = fe_mul(fe_sub(p.Y, p.X), q.ymx);
+    fe TT = fe_mul(p.T, q.xy2d);
+    fe ZZ2 = fe_add(p.Z, p.Z);
+    fe E = fe_sub(PP, MM), H = fe_add(PP, MM), G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
+    ge r;
+    r.X = fe_mul(E, F); r.Y = fe_mul(H, G); r.Z = fe_mul(G, F); r.T = fe_mul(E, H);
+    return r;
+}
+ACT_FN ge ge_add(const ge& p, const ge& q) { return ge_add_cached(p, ge_to_cached(q)); }
+ACT_FN ge ge_sub(const ge& p, const ge& q) { return ge_add_cached(p, ge_to_cached(ge_neg(q))); }
+
+// r = 2p.  T of the input is not read; T of the output is produced only when want_t (4S + 3M / 4M).
+ACT_FN ge ge_dbl(const ge& p, bool want_t) {
+    fe XX = fe_sq(p.X), YY = fe_sq(p.Y), ZZ = fe_sq(p.Z);
+    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe XpY2 = fe_sq(fe_add(p.X, p.Y));
+    fe Yc = fe_add(YY, XX), Zc = fe_sub(YY, XX);
+    fe Xc = fe_sub(XpY2, Yc), Tc = fe_sub(ZZ2, Zc);
+    ge r;
+    r.X = fe_mul(Xc, Tc); r.Y = fe_mul(Yc, Zc); r.Z = fe_mul(Zc, Tc);
+    if (want_t) r.T = fe_mul(Xc, Yc); else r.T = fe_zero();
+    return r;
+}
+
+// branch-free negate-if of table entries (negation swaps y+x / y-x and flips the sign of the t term)
+ACT_FN ge_cached ge_cached_cneg(const ge_cached& q, u32 neg) {
+    ge_cached r;
+    r.YpX = fe_select(q.YpX, q.YmX, neg); r.YmX = fe_select(q.YmX, q.YpX, neg);
+    r.Z = q.Z; r.T2d = fe_select(q.T2d, fe_neg(q.T2d), neg);
+    return r;
+}
+ACT_FN ge_niels ge_niels_cneg(const ge_niels& q, u32 neg) {
+    ge_niels r;
+    r.ypx = fe_select(q.ypx, q.ymx, neg); r.ymx = fe_select(q.ymx, q.ypx, neg);
+    r.xy2d = fe_select(q.xy2d, fe_neg(q.xy2d), neg);
+    return r;
+}
+// affine Niels form of a point with Z = 1
+ACT_FN ge_niels ge_affine_to_niels(const fe& x, const fe& y) {
+    ge_niels r;
+    r.ypx = fe_add(y, x); r.ymx = fe_sub(y, x); r.xy2d = fe_mul(fe_mul(x, y), FE_D2);
+    return r;
+}
+ACT_FN ge_niels ge_to_niels(const ge& p) {
+    fe zi = fe_invert(p.Z);
+    return ge_affine_to_niels(fe_mul(p.X, zi), fe_mul(p.Y, zi));
+}
+ACT_FN ge ge_from_niels(const ge_niels& n) {  // only for tests / table checks
+    // y = (ypx+ymx)/2, x = (ypx-ymx)/2 : keep projective with Z = 2
+    ge r;
+    r.Y = fe_add(n.ypx, n.ymx); r.X = fe_sub(n.ypx, n.ymx); r.Z = fe_add(fe_one(), fe_one());
+    fe zi = fe_invert(r.Z);
+    fe x = fe_mul(r.X, zi), y = fe_mul(r.Y, zi);
+    r.X = x; r.Y = y; r.Z = fe_one(); r.T = fe_mul(x, y);
+    return r;
+}
+
+// ---- ristretto255 --------------------------------------------------------------------------------
+// RFC 9496 4.3.1 / dalek CompressedRistretto::decompress.  w = 8 little-endian words of the wire
+// bytes.  Returns 1 and the point (Z = 1) when the encoding is valid, else 0 (point = identity).
+ACT_NOINLINE u32 ristretto_decode_(ge* out, const u32* w) {
+    fe s = fe_from_words(w);
+    fe sc_ = fe_canon(s);
+    u32 canonical = ((w[7] >> 31) == 0);
+    ACT_UNROLL for (int i = 0; i < 8; i++) canonical &= (sc_.v[i] == (i == 7 ? (w[7] & 0x7fffffffu) : w[i]));
+    u32 negative = w[0] & 1u;
+    fe ss = fe_sq(s);
+    fe u1 = fe_sub(fe_one(), ss), u2 = fe_add(fe_one(), ss);
+    fe u2_sqr = fe_sq(u2);
+    fe v = fe_sub(fe_neg(fe_mul(FE_D, fe_sq(u1))), u2_sqr);
+    u32 ok;
+    fe I = fe_invsqrt(&ok, fe_mul(v, u2_sqr));
+    fe Dx = fe_mul(I, u2);
+    fe Dy = fe_mul(fe_mul(I, Dx), v);
+    fe x = fe_abs(fe_mul(fe_add(s, s), Dx));
+    fe y = fe_mul(u1, Dy);
+    fe t = fe_mul(x, y);
+    u32 valid = canonical & (negative ^ 1u) & ok & (fe_is_negative(t) ^ 1u) & (fe_is_zero(y) ^ 1u);
+    ge id = ge_identity();
+    out->X = fe_select(id.X, x, valid); out->Y = fe_select(id.Y, y, valid);
+    out->Z = fe_one(); out->T = fe_select(id.T, t, valid);
+    return valid;
+}
+// RFC 9496 4.3.2 / dalek RistrettoPoint::compress.  Writes 8 canonical little-endian words.
+ACT_NOINLINE void ristretto_encode_(u32* w, const ge* pp) {
+    ge p = *pp;
+    fe u1 = fe_mul(fe_add(p.Z, p.Y), fe_sub(p.Z, p.Y));
+    fe u2 = fe_mul(p.X, p.Y);
+    u32 dummy;
+    fe I = fe_invsqrt(&dummy, fe_mul(u1, fe_sq(u2)));
+    fe i1 = fe_mul(I, u1), i2 = fe_mul(I, u2);
+    fe z_inv = fe_mul(i1, fe_mul(i2, p.T));
+    fe iX = fe_mul(p.X, FE_SQRT_M1), iY = fe_mul(p.Y, FE_SQRT_M1);
+    fe ench = fe_mul(i1, FE_INVSQRT_A_MINUS_D);
+    u32 rotate = fe_is_negative(fe_mul(p.T, z_inv));
+    fe X = fe_select(p.X, iY, rotate), Y = fe_select(p.Y, iX, rotate);
+    fe den_inv = fe_select(i2, ench, rotate);
+    Y = fe_cneg(Y, fe_is_negative(fe_mul(X, z_inv)));
+    fe s = fe_abs(fe_mul(den_inv, fe_sub(p.Z, Y)));
+    fe_to_words(w, s);
+}
+// RFC 9496 4.3.4 MAP / dalek elligator_ristretto_flavor
+ACT_NOINLINE void ristretto_elligator_(ge* out, const fe* r0p) {
+    fe r0 = *r0p;
+    fe one = fe_one(), minus_one = fe_neg(fe_one());
+    fe r = fe_mul(FE_SQRT_M1, fe_sq(r0));
+    fe u = fe_mul(fe_add(r, one), FE_ONE_MINUS_D_SQ);
+    fe v = fe_mul(fe_sub(minus_one, fe_mul(r, FE_D)), fe_add(r, FE_D));
+    u32 was_square;
+    fe s = fe_sqrt_ratio_i(&was_square, u, v);
+    fe s_prime = fe_mul(s, r0);
+    s_prime = fe_cneg(s_prime, fe_is_negative(s_prime) ^ 1u);
+    s = fe_select(s_prime, s, was_square);
+    fe c = fe_select(r, minus_one, was_square);
+    fe N = fe_sub(fe_mul(fe_mul(c, fe_sub(r, one)), FE_D_MINUS_ONE_SQ), v);
+    fe ss = fe_sq(s);
+    fe w0 = fe_mul(fe_add(s, s), v);
+    fe w1 = fe_mul(N, FE_SQRT_AD_MINUS_ONE);
+    fe w2 = fe_sub(one, ss), w3 = fe_add(one, ss);
+    out->X = fe_mul(w0, w3); out->Y = fe_mul(w2, w1); out->Z = fe_mul(w1, w3); out->T = fe_mul(w0, w2);
+}
+// RistrettoPoint::from_uniform_bytes: 16 little-endian words
+ACT_FN ge ristretto_from_uniform(const u32* w) {
+    fe r1 = fe_from_words(w), r2 = fe_from_words(w + 8);
+    ge P1, P2;
+    ristretto_elligator_(&P1, &r1);
+    ristretto_elligator_(&P2, &r2);
+    return ge_add(P1, P2);
+}
+// `point == RistrettoPoint::identity()` (src/lib.rs:787): X1*Y2 == Y1*X2 || X1*X2 == Y1*Y2 with (0,1)
+ACT_FN u32 ristretto_is_identity(const ge& p) { return fe_is_zero(p.X) | fe_is_zero(p.Y); }

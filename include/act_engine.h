@@ -1,0 +1,139 @@
+/*
+ * act_engine.h -- C ABI of the B200 batch engine for the issuer side of anonymous-credit-tokens.
+ *
+ * The reference crate (Rust, /root/reference) has no FFI boundary of its own: the hot path sits
+ * behind its public methods.  Each entry point below is what a `-sys` crate would bind in order
+ * to offer `batch_issue` / `batch_verify_spend_and_refund` over slices:
+ *
+ *   act_params_derive                  = Params::new                          src/lib.rs:291-354
+ *   act_batch_issue[_dev]              = n x PrivateKey::issue                src/lib.rs:621-663
+ *   act_batch_verify_spend_and_refund  = n x PrivateKey::refund               src/lib.rs:781-869
+ *                                        (+ SpendProof::nullifier             src/lib.rs:720-722)
+ *   act_batch_issuance_check[_dev]     = n x PreIssuance::to_credit_token     src/lib.rs:528-562 (verification half)
+ *   act_batch_refund_check[_dev]       = n x PreRefund::to_credit_token       src/lib.rs:1217-1253 (verification half)
+ *   act_pack_* / act_encode_*          = from_cbor / to_cbor                  src/cbor.rs:94-465
+ *
+ * Records hold WIRE bytes: points are 32-byte compressed ristretto255 encodings (validated on the
+ * device exactly like CompressedRistretto::decompress, src/cbor.rs:62-77) and scalars are 32-byte
+ * little-endian values reduced mod l on the device (Scalar::from_bytes_mod_order, src/cbor.rs:80-91).
+ *
+ *   IssuanceRequest  128 B : K | gamma | k_bar | r_bar                       (src/lib.rs:376-385)
+ *   IssuanceResponse 160 B : A | e | gamma | z | c                           (src/lib.rs:572-583)
+ *   SpendProof     16832 B : k | s | A' | B_bar | com[128] | gamma | e_bar | r2_bar | r3_bar | c_bar |
+ *                            r_bar | w00 | w01 | gamma0[128] | z[128][2] | k_bar | s_bar   (src/lib.rs:673-708)
+ *   Refund           128 B : A* | e* | gamma | z                             (src/lib.rs:1161-1170)
+ *   rnd              128 B : the 64 bytes Scalar::random would draw for e, then the 64 for alpha
+ *                            (src/lib.rs:643,649 / :846,852); ignored for rejected requests.
+ *
+ * Per-request outcome in status[i]:
+ *   0        Ok
+ *   1..9     1 + discriminant of the reference's `Error` (src/lib.rs:102-112):
+ *            1 InvalidIssuanceRequestProof, 2 InvalidIssuanceResponseProof, 3 DoubleSpendError,
+ *            4 InvalidRefundProof, 5 InvalidRefundResponseProof, 6 IdentityPointError,
+ *            7 InvalidClientSpendProof, 8 AmountTooBigError, 9 ScalarOutOfRangeError
+ *   0x81     a point failed to decode  (CborError::InvalidValue("invalid Ristretto point"))
+ *   0x82     CBOR structure error      (CborError::InvalidStructure)   -- only from act_pack_*
+ *   0x83     CBOR parse error          (CborError::Ciborium)           -- only from act_pack_*
+ * Outputs of rejected requests are zero-filled.
+ *
+ * Return value of every function: 0 on success, negative on a whole-call failure (bad argument,
+ * CUDA error); act_last_error() describes it.  There is no CPU fallback: without a usable CUDA
+ * device every compute entry point fails.
+ *
+ * Threading: one engine may be used from one host thread at a time.  Engines are independent.
+ * The caller owns every buffer.  Host-buffer entry points copy H2D/D2H internally (pinned buffers
+ * from act_host_alloc make those copies asynchronous); `_dev` entry points take device pointers
+ * (16-byte aligned) and a CUDA stream (cudaStream_t cast to void*, NULL = the engine's stream) and
+ * are asynchronous with respect to the host.
+ */
+#ifndef ACT_ENGINE_H
+#define ACT_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACT_REQUEST_BYTES 128
+#define ACT_RESPONSE_BYTES 160
+#define ACT_PROOF_BYTES 16832
+#define ACT_REFUND_BYTES 128
+#define ACT_RND_BYTES 128
+#define ACT_COM_BYTES 4096
+
+typedef struct act_engine act_engine;
+
+#if defined(__GNUC__)
+#define ACT_API __attribute__((visibility("default")))
+#else
+#define ACT_API
+#endif
+
+ACT_API const char* act_last_error(void);
+ACT_API int act_device_count(void);
+
+/* Params::new: H1 | H2 | H3 encodings (96 bytes).  Runs on `device`. */
+ACT_API int act_params_derive(int device, const char* org, const char* service, const char* deployment, const char* version,
+                      uint8_t h[96]);
+
+/* Engine for one (Params, PrivateKey) pair on one GPU.  h = H1|H2|H3 encodings, sk_x = secret scalar
+ * (reduced mod l), pk_w = encoding of W = G*x.  Fails if any point does not decode. */
+ACT_API int act_engine_create(act_engine** out, int device, const uint8_t h[96], const uint8_t sk_x[32], const uint8_t pk_w[32]);
+/* Zeroises the device and host copies of the secret and frees everything. */
+ACT_API void act_engine_destroy(act_engine* e);
+ACT_API int act_engine_device(const act_engine* e);
+/* PrivateKey::public: W = G*x for a given secret (convenience for key set-up). */
+ACT_API int act_public_key(int device, const uint8_t sk_x[32], uint8_t pk_w[32]);
+
+/* Pinned host memory helpers. */
+ACT_API void* act_host_alloc(size_t bytes);
+ACT_API void act_host_free(void* p);
+
+/* ---- host-buffer entry points (synchronous) ---- */
+ACT_API int act_batch_issue(act_engine* e, size_t n, const uint8_t* req /* n*128 */, const uint8_t* c /* n*32 */,
+                    const uint8_t* rnd /* n*128 */, uint8_t* resp /* n*160 */, uint8_t* status /* n */);
+ACT_API int act_batch_verify_spend_and_refund(act_engine* e, size_t n, const uint8_t* proofs /* n*16832 */,
+                                      const uint8_t* rnd /* n*128 */, uint8_t* refunds /* n*128 */,
+                                      uint8_t* nullifiers /* n*32 */, uint8_t* status /* n */);
+ACT_API int act_batch_issuance_check(act_engine* e, size_t n, const uint8_t* K /* n*32 */, const uint8_t* resp /* n*160 */,
+                             uint8_t* status /* n */);
+ACT_API int act_batch_refund_check(act_engine* e, size_t n, const uint8_t* com /* n*4096 */, const uint8_t* refund /* n*128 */,
+                           uint8_t* status /* n */);
+
+/* ---- device-buffer entry points (asynchronous on `stream`) ---- */
+ACT_API int act_batch_issue_dev(act_engine* e, size_t n, const void* req, const void* c, const void* rnd, void* resp,
+                        void* status, void* stream);
+ACT_API int act_batch_verify_spend_and_refund_dev(act_engine* e, size_t n, const void* proofs, const void* rnd, void* refunds,
+                                          void* nullifiers, void* status, void* stream);
+ACT_API int act_batch_issuance_check_dev(act_engine* e, size_t n, const void* K, const void* resp, void* status, void* stream);
+ACT_API int act_batch_refund_check_dev(act_engine* e, size_t n, const void* com, const void* refund, void* status, void* stream);
+
+/* Number of kernel launches issued by this engine since creation (for bench accounting). */
+ACT_API uint64_t act_engine_launch_count(const act_engine* e);
+
+/* Device self-test of the arithmetic layers against built-in known answers; 0 = pass. */
+ACT_API int act_selftest(int device);
+
+/* ---- CBOR front doors (host only; src/cbor.rs) ----
+ * act_pack_*: decode n CBOR items (items[i], lens[i]) into fixed records; status[i] = 0, 0x82 or 0x83.
+ * Point validity is NOT checked here (it is checked on the device and reported as 0x81).
+ * act_encode_*: write the canonical CBOR encoding of a record; returns the encoded length. */
+ACT_API int act_pack_issuance_requests_cbor(size_t n, const uint8_t* const* items, const size_t* lens, uint8_t* req, uint8_t* status);
+ACT_API int act_pack_spend_proofs_cbor(size_t n, const uint8_t* const* items, const size_t* lens, uint8_t* proofs, uint8_t* status);
+ACT_API int act_pack_issuance_responses_cbor(size_t n, const uint8_t* const* items, const size_t* lens, uint8_t* resp, uint8_t* status);
+ACT_API int act_pack_refunds_cbor(size_t n, const uint8_t* const* items, const size_t* lens, uint8_t* refunds, uint8_t* status);
+#define ACT_CBOR_REQUEST_BYTES 141
+#define ACT_CBOR_RESPONSE_BYTES 176
+#define ACT_CBOR_PROOF_BYTES 18036
+#define ACT_CBOR_REFUND_BYTES 141
+ACT_API size_t act_encode_issuance_request_cbor(const uint8_t req[128], uint8_t out[141]);
+ACT_API size_t act_encode_issuance_response_cbor(const uint8_t resp[160], uint8_t out[176]);
+ACT_API size_t act_encode_spend_proof_cbor(const uint8_t* proof /* 16832 */, uint8_t* out /* 18036 */);
+ACT_API size_t act_encode_refund_cbor(const uint8_t refund[128], uint8_t out[141]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACT_ENGINE_H */

@@ -1,0 +1,169 @@
+"""Deterministic synthetic corpora for parity tests and the bench: valid requests/proofs produced by the
+oracle's fixture generators (request, prove_spend) plus one generator per mutation class of the
+reference's own tests (/root/reference src/tests.rs).
+
+TEST INFRASTRUCTURE ONLY (uses oracle/).
+"""
+import os
+
+import numpy as np
+
+import oracle_lib as O
+
+ELL = 2**252 + 27742317777372353535851937790883648493
+P25519 = 2**255 - 19
+PROOF_BYTES = O.PROOF_BYTES
+BENCH_PARAMS = ("bench-org", "bench-service", "bench-env", "2024-01-01")   # benches/benchmark.rs:10-15
+TEST_PARAMS = ("test-org", "test-service", "test-env", "2024-01-01")       # src/tests.rs:59
+
+
+def xof(seed: bytes, n: int) -> bytes:
+    return O.blake3(seed, n)
+
+
+def sc_bytes(x):
+    return (x % ELL).to_bytes(32, "little")
+
+
+def sc_int(b):
+    return int.from_bytes(bytes(b), "little")
+
+
+def make_ctx(params=TEST_PARAMS, key_seed=b"act-b200-key-0"):
+    h = O.params_derive(*params)
+    x, w = O.keygen(xof(key_seed, 64))
+    return O.Ctx(h, x, w)
+
+
+def gen_valid(ctx, n, seed=b"corpus-0", credits=(20, 1000), threads=None, want_proofs=True):
+    """n independent issue->token->prove_spend trips.  credits uniform in [lo,hi), charge uniform in [1,c-1]
+    (benches/benchmark.rs:60,178,194-201)."""
+    threads = threads or min(os.cpu_count() or 1, 32)
+    rs = np.random.RandomState(int.from_bytes(xof(seed, 4), "little"))
+    seeds = np.frombuffer(xof(seed + b"/seeds", 64 * n), dtype=np.uint8).copy()
+    cr = rs.randint(credits[0], credits[1], size=n).astype(np.uint64)
+    ch = np.array([rs.randint(1, max(2, int(c))) for c in cr], dtype=np.uint64)
+    out = ctx.generate(seeds, cr, ch, threads=threads, want_proofs=want_proofs)
+    out["rnd"] = np.frombuffer(xof(seed + b"/rnd", 128 * n), dtype=np.uint8).copy()
+    out["credits"], out["charges"] = cr, ch
+    return out
+
+
+# ---- invalid point encodings (RFC 9496 A.3 classes; src/cbor.rs:62-77) ----
+def bad_point_encodings():
+    out = []
+    out.append((P25519).to_bytes(32, "little"))            # non-canonical field element (s = p)
+    out.append((P25519 + 2).to_bytes(32, "little"))        # non-canonical
+    out.append((2**255 + 4).to_bytes(32, "little"))        # top bit set
+    out.append(b"\xff" * 32)
+    out.append((1).to_bytes(32, "little"))                 # negative (odd) s
+    # non-square / negative-t / y=0 cases from RFC 9496 A.3
+    for hx in ("26948d35ca62e643e26a83177332e6b6afeb9d08e4268b650f1f5bbd8d81d371",
+               "4eac077a713c57b4f4397629a4145982c661f48044dd3f96427d40b147d9742f",
+               "de6a7b00deadbeefde6a7b00deadbeefde6a7b00deadbeefde6a7b00deadbe6f",
+               "bcab477be20861e01e4a0e295284146a510150d9817763caf1a6f4b422d67042",
+               "2a292df7e32cababbd9de088d1d1abec9fc0440f637ed2fba145094dc14bea08",
+               "f4a9e534fc0d216c44b218fa0c42d99635a0127ee2e53c712f70609649fdff22",
+               "8268436f8c4126196cf64b3c7ddbda90746a378625f9813dd9b8457077256731",
+               "2810e5cbc2cc4d4eece54f61c6f69758e289aa7ab440b3cbeaa21995c2f4232b",
+               "3eb858e78f5a7254d8c9731174a94f76755fd3941c0ac93735c07ba14579630e",
+               "a45fdc55c76448c049a1ab33f17023edfb2be3581e9c7aade8a6125215e04220",
+               "d483fe813c6ba647ebbfd3ec41adca1c6130c2beeee9d9bf065c8d151c5f396e",
+               "8a2e1d30050198c65a54483123960ccc38aef6848e1ec8f5f780e8523769ba32",
+               "32888462f8b486c68ad7dd9610be5192bbeaf3b443951ac1a8118419d9fa097b",
+               "227142501b9d4355ccba290404bde41575b037693cef1f438c47f8fbf35d1165",
+               "5c37cc491da847cfeb9281d407efc41e15144c876e0170b499a96a22ed31e01e",
+               "445425117cb8c90edcbc7c1cc0e74f747f2c1efa5630a967c64f287792a48a4b"):
+        out.append(bytes.fromhex(hx))
+    return out
+
+
+def mutate_requests(ctx, base, seed=b"mut-req"):
+    """Returns (req, cs, rnd, expected_status, label) arrays built from valid requests `base` (dict of gen_valid)."""
+    req = base["req"].reshape(-1, 128).copy(); cs = base["cs"].reshape(-1, 32).copy(); rnd = base["rnd"].reshape(-1, 128).copy()
+    n = len(req)
+    expect = np.zeros(n, np.uint8); labels = ["valid"] * n
+    bad = bad_point_encodings()
+    rs = np.random.RandomState(7)
+    for i in range(n):
+        kind = i % 8
+        if kind == 1:      # k_bar += 1  (src/tests.rs:583-593)
+            req[i, 64:96] = np.frombuffer(sc_bytes(sc_int(req[i, 64:96]) + 1), np.uint8); expect[i] = 1; labels[i] = "k_bar+1"
+        elif kind == 2:    # random K and gamma (src/tests.rs:1945-1953)
+            req[i, 0:32] = np.frombuffer(O.scalarmult_base(xof(seed + bytes([i & 255, 1]), 32)), np.uint8)
+            req[i, 32:64] = np.frombuffer(O.sc_reduce32(xof(seed + bytes([i & 255, 2]), 32)), np.uint8); expect[i] = 1; labels[i] = "random K,gamma"
+        elif kind == 3:    # malformed point
+            req[i, 0:32] = np.frombuffer(bad[(i // 8) % len(bad)], np.uint8); expect[i] = 0x81; labels[i] = "bad K"
+        elif kind == 4:    # non-canonical scalar encodings still accept (src/cbor.rs:80-91)
+            for off in (32, 64, 96):
+                v = sc_int(req[i, off:off + 32]) + ELL
+                if v < 2**256:
+                    req[i, off:off + 32] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
+            v = sc_int(cs[i]) + ELL
+            cs[i] = np.frombuffer(v.to_bytes(32, "little"), np.uint8); labels[i] = "non-canonical scalars"
+        elif kind == 5:    # single random bit flip somewhere in the scalars
+            b = 32 * 8 + rs.randint(0, 96 * 8)
+            req[i, b // 8] ^= 1 << (b % 8); expect[i] = 255; labels[i] = "bit flip"   # 255 = whatever the oracle says
+        elif kind == 6:    # gamma += t
+            req[i, 32:64] = np.frombuffer(sc_bytes(sc_int(req[i, 32:64]) + 1 + rs.randint(0, 1 << 30)), np.uint8); expect[i] = 1; labels[i] = "gamma+t"
+    return req.reshape(-1), cs.reshape(-1), rnd.reshape(-1), expect, labels
+
+
+def _set(pf, idx, val32):
+    pf[32 * idx:32 * idx + 32] = np.frombuffer(bytes(val32), np.uint8)
+
+
+def _get(pf, idx):
+    return bytes(pf[32 * idx:32 * idx + 32])
+
+
+def mutate_proofs(ctx, base, seed=b"mut-pf"):
+    """Adversarial spend corpus: (proofs, rnd, expected_status, labels).  expected 255 = defer to the oracle."""
+    proofs = base["proofs"].reshape(-1, PROOF_BYTES).copy(); rnd = base["rnd"].reshape(-1, 128).copy()
+    n = len(proofs)
+    expect = np.zeros(n, np.uint8); labels = ["valid"] * n
+    bad = bad_point_encodings()
+    rs = np.random.RandomState(11)
+    for i in range(n):
+        pf = proofs[i]
+        kind = i % 12
+        if kind == 1:      # s replaced (src/tests.rs:631-638)
+            _set(pf, 1, sc_bytes(sc_int(_get(pf, 1)) + 1)); expect[i] = 7; labels[i] = "s changed"
+        elif kind == 2:    # gamma += t (src/tests.rs:1701-1708)
+            _set(pf, 132, sc_bytes(sc_int(_get(pf, 132)) + 1 + rs.randint(0, 1 << 30))); expect[i] = 7; labels[i] = "gamma+t"
+        elif kind == 3:    # a_prime = identity (src/tests.rs:868-872)
+            _set(pf, 2, bytes(32)); expect[i] = 6; labels[i] = "A' identity"
+        elif kind == 4:    # malformed com[j]
+            _set(pf, 4 + rs.randint(0, 128), bad[(i // 12) % len(bad)]); expect[i] = 0x81; labels[i] = "bad com"
+        elif kind == 5:    # malformed A' or B_bar
+            _set(pf, 2 + (i // 12) % 2, bad[(i // 12 + 3) % len(bad)]); expect[i] = 0x81; labels[i] = "bad A'/B"
+        elif kind == 6:    # non-canonical scalars accept; nullifier is the reduced value
+            for idx in (0, 133, 140 + rs.randint(0, 128), 268 + rs.randint(0, 256), 525):
+                v = sc_int(_get(pf, idx)) + ELL
+                if v < 2**256:
+                    _set(pf, idx, v.to_bytes(32, "little"))
+            labels[i] = "non-canonical scalars"
+        elif kind == 7:    # exact replay of the previous valid proof (caller's job to catch; refund still Ok)
+            if i >= 7:
+                proofs[i] = proofs[i - 7]; labels[i] = "replay"
+        elif kind == 8:    # random bit flip in a scalar field of the range proof
+            idx = 140 + rs.randint(0, 384); b = rs.randint(0, 252)
+            pf[32 * idx + b // 8] ^= 1 << (b % 8); expect[i] = 7; labels[i] = "range scalar flip"
+        elif kind == 9:    # valid point swapped in for a commitment (com[j] := com[j'] )
+            j = rs.randint(0, 127); _set(pf, 4 + j, _get(pf, 5 + j)); expect[i] = 255; labels[i] = "com swapped"
+        elif kind == 10:   # identity encoding inside com[] is a VALID point: proof fails, not a decode error
+            _set(pf, 4 + rs.randint(0, 128), bytes(32)); expect[i] = 7; labels[i] = "com identity"
+        elif kind == 11:   # k changed (nullifier forgery)
+            _set(pf, 0, sc_bytes(sc_int(_get(pf, 0)) + 1)); expect[i] = 7; labels[i] = "k changed"
+    return proofs.reshape(-1), rnd.reshape(-1), expect, labels
+
+
+def overspend_proofs(ctx, n, seed=b"overspend"):
+    """prove_spend run with s > c (src/tests.rs:366-374,1540-1547) -> InvalidClientSpendProof."""
+    rs = np.random.RandomState(5)
+    seeds = np.frombuffer(xof(seed, 64 * n), dtype=np.uint8).copy()
+    cr = rs.randint(5, 500, size=n).astype(np.uint64)
+    ch = (cr + rs.randint(1, 100, size=n).astype(np.uint64)).astype(np.uint64)
+    out = ctx.generate(seeds, cr, ch, threads=min(os.cpu_count() or 1, 16))
+    out["rnd"] = np.frombuffer(xof(seed + b"/rnd", 128 * n), dtype=np.uint8).copy()
+    return out
