@@ -56,7 +56,8 @@ EXPORTED_SYMBOLS = [
     "act_engine_device", "act_public_key", "act_host_alloc", "act_host_free", "act_batch_issue",
     "act_batch_verify_spend_and_refund", "act_batch_issuance_check", "act_batch_refund_check",
     "act_batch_issue_dev", "act_batch_verify_spend_and_refund_dev", "act_batch_issuance_check_dev",
-    "act_batch_refund_check_dev", "act_engine_launch_count", "act_selftest",
+    "act_batch_refund_check_dev", "act_engine_launch_count", "act_selftest", "act_engine_set_timing",
+    "act_engine_get_timing", "act_measure_int_mul_peak",
     "act_pack_issuance_requests_cbor", "act_pack_spend_proofs_cbor", "act_pack_issuance_responses_cbor",
     "act_pack_refunds_cbor", "act_encode_issuance_request_cbor", "act_encode_issuance_response_cbor",
     "act_encode_spend_proof_cbor", "act_encode_refund_cbor",
@@ -99,6 +100,9 @@ def load_library():
     lib.act_batch_refund_check_dev.argtypes = [vp, sz, vp, vp, vp, vp]; lib.act_batch_refund_check_dev.restype = i32
     lib.act_engine_launch_count.argtypes = [vp]; lib.act_engine_launch_count.restype = u64
     lib.act_selftest.argtypes = [i32]; lib.act_selftest.restype = i32
+    lib.act_engine_set_timing.argtypes = [vp, i32]; lib.act_engine_set_timing.restype = i32
+    lib.act_engine_get_timing.argtypes = [vp, vp, vp]; lib.act_engine_get_timing.restype = i32
+    lib.act_measure_int_mul_peak.argtypes = [i32, vp]; lib.act_measure_int_mul_peak.restype = i32
     for name in ("act_pack_issuance_requests_cbor", "act_pack_spend_proofs_cbor", "act_pack_issuance_responses_cbor", "act_pack_refunds_cbor"):
         f = getattr(lib, name); f.argtypes = [sz, vp, vp, vp, vp]; f.restype = i32
     for name in ("act_encode_issuance_request_cbor", "act_encode_issuance_response_cbor", "act_encode_spend_proof_cbor", "act_encode_refund_cbor"):
@@ -128,6 +132,17 @@ def device_count():
 def selftest(device=0):
     """Device self-test of the PTX field arithmetic against built-in known answers."""
     _check(load_library().act_selftest(device), "act_selftest")
+
+
+KERNEL_KINDS = ["spend_range", "spend_head", "spend_chunk_hash", "spend_finish", "refund_sign", "issue",
+                "issuance_check", "refund_check"]
+
+
+def measure_int_mul_peak(device=0):
+    """Measured integer-multiply roofline: sustained 32x32+64->64 multiply-adds per second (IMAD.WIDE.U32)."""
+    v = C.c_double(0)
+    _check(load_library().act_measure_int_mul_peak(device, C.addressof(v)), "act_measure_int_mul_peak")
+    return v.value
 
 
 class Params:
@@ -196,6 +211,15 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.act_engine_launch_count(self._h))
+
+    def set_timing(self, enable=True):
+        _check(self.lib.act_engine_set_timing(self._h, 1 if enable else 0), "act_engine_set_timing")
+
+    def get_timing(self):
+        """{kernel kind: (total device ms, launches)} since the last call (synchronises)."""
+        ms = (C.c_double * 8)(); cnt = (C.c_uint64 * 8)()
+        _check(self.lib.act_engine_get_timing(self._h, C.addressof(ms), C.addressof(cnt)), "act_engine_get_timing")
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(KERNEL_KINDS)}
 
     # ---- host buffers (numpy uint8) ----
     def batch_issue(self, requests, cs, rnd):

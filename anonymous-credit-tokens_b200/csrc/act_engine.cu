@@ -180,7 +180,22 @@ struct act_engine {
     spend_scratch scratch[2];
     io_slot io[2];
     uint64_t launches = 0;
+    // optional per-kernel device timing (CUDA events on the launching stream)
+    bool timing = false;
+    struct timed { int kind; cudaEvent_t a, b; };
+    std::vector<timed> events;
 };
+enum { K_RANGE = 0, K_HEAD, K_CHUNK, K_FINISH, K_SIGN, K_ISSUE, K_ISSUANCE_CHECK, K_REFUND_CHECK, K_KINDS };
+
+// LAUNCH(e, kind, stream, kernel<<<...>>>(...)) : counts the launch and, when timing is on, brackets it with events
+#define LAUNCH(e, kind, st, ...)                                                              \
+    do {                                                                                      \
+        act_engine::timed t_{kind, nullptr, nullptr};                                         \
+        if ((e)->timing) { cudaEventCreate(&t_.a); cudaEventCreate(&t_.b); cudaEventRecord(t_.a, st); } \
+        __VA_ARGS__;                                                                          \
+        if ((e)->timing) { cudaEventRecord(t_.b, st); (e)->events.push_back(t_); }            \
+        (e)->launches += 1;                                                                   \
+    } while (0)
 
 static int ensure(u8** p, size_t* cap, size_t need) {
     if (*cap >= need) return 0;
@@ -349,6 +364,71 @@ extern "C" int act_public_key(int device, const uint8_t sk_x[32], uint8_t pk_w[3
     return 0;
 }
 
+extern "C" int act_engine_set_timing(act_engine* e, int enable) {
+    if (!e) return fail_msg("null engine");
+    e->timing = enable != 0;
+    return 0;
+}
+// Sums (and clears) the device time of every launch recorded since the last call, per kernel kind:
+// 0 spend_range, 1 spend_head, 2 spend_chunk(hash), 3 spend_finish, 4 refund_sign, 5 issue, 6 issuance_check, 7 refund_check.
+extern "C" int act_engine_get_timing(act_engine* e, double ms[8], uint64_t count[8]) {
+    if (!e || !ms || !count) return fail_msg("act_engine_get_timing: null argument");
+    CK(cudaSetDevice(e->device));
+    for (int k = 0; k < K_KINDS; k++) { ms[k] = 0; count[k] = 0; }
+    for (auto& t : e->events) {
+        CK(cudaEventSynchronize(t.b));
+        float f = 0;
+        CK(cudaEventElapsedTime(&f, t.a, t.b));
+        ms[t.kind] += f; count[t.kind] += 1;
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    e->events.clear();
+    return 0;
+}
+
+// Integer-multiply roofline of this GPU: sustained rate of independent 32x32+64->64 multiply-adds
+// (IMAD.WIDE.U32), in limb-MACs per second.
+#define PEAK_ITER 4096
+__global__ void __launch_bounds__(256) int_mul_peak_kernel(u32* out, u32 a0, u32 b0) {
+    u32 a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+    u64 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = i;
+#pragma unroll 1
+    for (int it = 0; it < PEAK_ITER; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (u32)s ^ (u32)(s >> 32);
+}
+extern "C" int act_measure_int_mul_peak(int device, double* limb_macs_per_s) {
+    if (!limb_macs_per_s) return fail_msg("null argument");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    int blocks = p.multiProcessorCount * 8;
+    u32* out = nullptr;
+    CK(cudaMalloc((void**)&out, (size_t)blocks * 256 * 4));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    double best = 1e30;
+    for (int r = 0; r < 6; r++) {
+        CK(cudaEventRecord(a));
+        int_mul_peak_kernel<<<blocks, 256>>>(out, 3, 5);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    *limb_macs_per_s = (double)blocks * 256 * PEAK_ITER * 8 / (best * 1e-3);
+    return 0;
+}
+
 extern "C" int act_selftest(int device) {
     CK(cudaSetDevice(device));
     u32* d_fail = nullptr;
@@ -371,8 +451,7 @@ extern "C" int act_batch_issue_dev(act_engine* e, size_t n, const void* req, con
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
-    issue_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)req, (const u32*)c, (const u32*)rnd, (u32*)resp, (u8*)status);
-    e->launches += 1;
+    LAUNCH(e, K_ISSUE, st, (issue_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)req, (const u32*)c, (const u32*)rnd, (u32*)resp, (u8*)status)));
     CK(cudaGetLastError());
     return 0;
 }
@@ -381,8 +460,7 @@ extern "C" int act_batch_issuance_check_dev(act_engine* e, size_t n, const void*
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
-    issuance_check_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)K, (const u32*)resp, (u8*)status);
-    e->launches += 1;
+    LAUNCH(e, K_ISSUANCE_CHECK, st, (issuance_check_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)K, (const u32*)resp, (u8*)status)));
     CK(cudaGetLastError());
     return 0;
 }
@@ -391,8 +469,7 @@ extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* c
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
-    refund_check_kernel<<<nblocks(n, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)com, (const u32*)refund, (u8*)status);
-    e->launches += 1;
+    LAUNCH(e, K_REFUND_CHECK, st, (refund_check_kernel<<<nblocks(n, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)com, (const u32*)refund, (u8*)status)));
     CK(cudaGetLastError());
     return 0;
 }
@@ -400,12 +477,11 @@ extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* c
 static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, size_t m, const u32* proofs, const u32* rnd,
                               u32* refunds, u32* nullifiers, u8* status) {
     CK(cudaMemsetAsync(s->flags, 0, m * 4, st));
-    spend_range_kernel<<<(unsigned)m, ACT_L, 0, st>>>(e->d_ctx, proofs, s->items, s->com_niels, s->flags);
-    spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->kprime, s->flags);
-    spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, s->items, s->cvs);
-    spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status);
-    refund_sign_kernel<<<nblocks(m, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, m, proofs, rnd, s->kprime, status, refunds, nullifiers);
-    e->launches += 5;
+    LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<(unsigned)m, ACT_L, 0, st>>>(e->d_ctx, proofs, s->items, s->com_niels, s->flags)));
+    LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->kprime, s->flags)));
+    LAUNCH(e, K_CHUNK, st, (spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, s->items, s->cvs)));
+    LAUNCH(e, K_FINISH, st, (spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status)));
+    LAUNCH(e, K_SIGN, st, (refund_sign_kernel<<<nblocks(m, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, m, proofs, rnd, s->kprime, status, refunds, nullifiers)));
     CK(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 batch engine (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n-spend N] [--n-issue N]
+
+One "step" = one pass of `batch_verify_spend_and_refund` over one batch of synthetic SpendProofs
+(default 1,048,576 per GPU = BASELINE.json configs[2]; weak scaling, so N=8 is the 8M-proof batch of
+configs[3]).  Prints ONE JSON line (rank 0):
+
+  value      : spend verify+refund per second, whole job, inputs resident in HBM, device-timed
+  e2e        : same metric through the C ABI with pinned HOST buffers (H2D + kernels + D2H in the timed region)
+  issue      : batch_issue throughput (configs[1]) measured the same two ways
+  roofline   : dominant kernel (spend_range_kernel) vs the measured integer-multiply roofline
+  cpu_baseline: the oracle (port of the reference's algorithm) timed on this box's host cores
+
+--impl reference times the reference's own CPU algorithm (the C oracle port: the crate itself cannot be built
+in this image -- no Rust toolchain) with all host threads on a bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "spend_verify_refund_per_sec"
+UNIT = "proofs/s"
+# algorithmic work per unit: 32x32->64 limb multiply-accumulates
+LIMB_MACS_PER_SPEND = 4.8e7
+LIMB_MACS_PER_SPEND_RANGE = 4.66e7   # share of the 256 range-proof commitments + 128 decodes (stage 1 kernel)
+LIMB_MACS_PER_ISSUE = 7.0e5
+PROOF_BYTES = 16832
+UNIQUE_PROOFS = 2048                 # unique valid proofs synthesised on the CPU, tiled to the batch size
+UNIQUE_REQUESTS = 16384
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth(ctx, n_unique_proofs, n_unique_req, threads):
+    import corpus
+    t0 = time.time()
+    base = corpus.gen_valid(ctx, n_unique_proofs, seed=b"bench-spend", credits=(20, 1000), threads=threads)
+    reqs = corpus.gen_valid(ctx, n_unique_req, seed=b"bench-issue", credits=(10, 1000), threads=threads, want_proofs=False)
+    log(f"[bench] synthesised {n_unique_proofs} proofs + {n_unique_req} requests on {threads} host threads in {time.time() - t0:.1f}s")
+    return base, reqs
+
+
+def cpu_baseline(ctx, base, reqs, threads, budget_s=8.0):
+    """Oracle (restated reference algorithm) on the host cores: typed refund()/issue() closures as in benches/benchmark.rs."""
+    n1 = 24
+    t1, ok = ctx.time_refund_typed(base["proofs"][:n1 * PROOF_BYTES], base["rnd"][:n1 * 128], threads=1, reps=1)
+    assert ok == n1
+    per = t1 / n1
+    nall = min(len(base["proofs"]) // PROOF_BYTES, max(threads * 4, int(budget_s / per) * threads // 1))
+    nall = max(threads, (nall // threads) * threads)
+    tall, ok = ctx.time_refund_typed(base["proofs"][:nall * PROOF_BYTES], base["rnd"][:nall * 128], threads=threads, reps=1)
+    assert ok == nall
+    ni = 2048
+    ti1, ok = ctx.time_issue_typed(reqs["req"][:ni * 128], reqs["cs"][:ni * 32], reqs["rnd"][:ni * 128], threads=1, reps=1)
+    nia = min(len(reqs["req"]) // 128, 2048 * threads)
+    tia, ok = ctx.time_issue_typed(reqs["req"][:nia * 128], reqs["cs"][:nia * 32], reqs["rnd"][:nia * 128], threads=threads, reps=4)
+    return {
+        "value": nall / tall, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": f"{nall} typed refund() calls on {threads} threads ({tall:.2f}s); 1 thread: {n1} calls",
+        "value_1thread": n1 / t1,
+        "issue": {"value": nia * 4 / tia, "unit": "issues/s", "value_1thread": ni / ti1},
+    }
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import corpus
+    threads = os.cpu_count() or 1
+    ctx = corpus.make_ctx(corpus.BENCH_PARAMS)
+    n = max(threads * 2, 64)
+    base = corpus.gen_valid(ctx, n, seed=b"bench-spend", credits=(20, 1000), threads=threads)
+    times = []
+    for s in range(args.warmup + args.steps):
+        t, ok = ctx.time_refund_typed(base["proofs"], base["rnd"], threads=threads, reps=1)
+        assert ok == n
+        if s >= args.warmup:
+            times.append(t)
+    tot = sum(times)
+    v = n * len(times) / tot
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (int)",
+        "data": "synthetic", "config": {"workload": f"PrivateKey::refund on {n} valid SpendProofs per step (bounded sample of configs[2]), L=128, bench params",
+                                       "note": "reference crate is Rust with un-vendored deps; no cargo/rustc in this image -> C port of its algorithm (oracle/act_oracle.c), "
+                                               "constant-time radix-16 scalar mults and the 128-mult K' as in src/lib.rs:781-869"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{n} typed refund() calls per step on {threads} threads"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-spend", type=int, default=1 << 20, help="SpendProofs per GPU per step")
+    ap.add_argument("--n-issue", type=int, default=1 << 20, help="IssuanceRequests per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import corpus
+    act = importlib.import_module("anonymous-credit-tokens_b200")
+    act.load_library()                      # fails loudly if the CUDA extension is missing
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    n, ni = args.n_spend, args.n_issue
+    threads = max(1, (os.cpu_count() or 1) // world)
+
+    # ---- synthetic inputs (oracle fixture generators), identical on every rank; each rank rotates its tiling ----
+    ctx = corpus.make_ctx(corpus.BENCH_PARAMS)
+    base, reqs = synth(ctx, UNIQUE_PROOFS, UNIQUE_REQUESTS, threads)
+    params = act.Params.new(*corpus.BENCH_PARAMS, device=local)
+    assert params.h == ctx.h, "Params::new differs from the oracle"
+    eng = act.Engine(params, act.PrivateKey(ctx.x, ctx.w), device=local)
+    peak = act.measure_int_mul_peak(local)
+
+    def tile_to(dst_t, src_np, rec, count, shift):
+        """fill device tensor with `count` records by tiling the unique set (rotated by `shift` records)."""
+        u = len(src_np) // rec
+        src = torch.from_numpy(np.roll(src_np.reshape(u, rec), -shift, axis=0).copy()).to(dev)
+        v = dst_t.view(-1, rec)
+        for off in range(0, count, u):
+            m = min(u, count - off)
+            v[off:off + m] = src[:m]
+
+    d_proofs = torch.empty(n * PROOF_BYTES, dtype=torch.uint8, device=dev)
+    d_rnd = torch.empty(n * 128, dtype=torch.uint8, device=dev)
+    tile_to(d_proofs, base["proofs"], PROOF_BYTES, n, rank * 7)
+    tile_to(d_rnd, base["rnd"], 128, n, rank * 7)
+    d_ref = torch.zeros(n * 128, dtype=torch.uint8, device=dev)
+    d_nul = torch.zeros(n * 32, dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(n, dtype=torch.uint8, device=dev)
+    if world > 1:
+        g_st = torch.empty(world * n, dtype=torch.uint8, device=dev)
+        g_nul = torch.empty(world * n * 32, dtype=torch.uint8, device=dev)
+    # a real (non-default) stream: the engine launches on it and torch's events are recorded on it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    def spend_step():
+        eng.batch_verify_spend_and_refund_dev(n, d_proofs.data_ptr(), d_rnd.data_ptr(), d_ref.data_ptr(), d_nul.data_ptr(), d_st.data_ptr(), stream)
+        if world > 1:   # the one collective on the path: gather accept bits and nullifiers (33 B / proof)
+            dist.all_gather_into_tensor(g_st, d_st)
+            dist.all_gather_into_tensor(g_nul, d_nul)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, warm, steps):
+        for _ in range(warm):
+            step_fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- value: device-resident, device-timed, per-kernel timing on ----
+    for _ in range(W):
+        spend_step()
+    barrier()
+    eng.set_timing(True)
+    eng.get_timing()
+    launches0 = eng.launch_count
+    with ClockSampler(local) as clk:
+        ms = timed(spend_step, 0, K)
+    ktimes = eng.get_timing()
+    eng.set_timing(False)
+    launches = eng.launch_count - launches0
+    clocks = clk.summary()
+    value = world * n * K / (ms * 1e-3)
+    # parity guard inside the bench: every proof of the valid batch accepted, refunds equal the oracle's for a sample
+    st_host = d_st.cpu().numpy()
+    assert (st_host == 0).all(), f"bench batch not fully accepted: {np.unique(st_host, return_counts=True)}"
+    chk = 4
+    o_ref, o_nul, o_st, _ = ctx.batch_refund(np.roll(base["proofs"].reshape(-1, PROOF_BYTES), -rank * 7, axis=0)[:chk].reshape(-1).copy(),
+                                             np.roll(base["rnd"].reshape(-1, 128), -rank * 7, axis=0)[:chk].reshape(-1).copy(), threads=chk)
+    assert (d_ref[:chk * 128].cpu().numpy() == o_ref).all() and (d_nul[:chk * 32].cpu().numpy() == o_nul).all(), "bench output differs from oracle"
+
+    rng_ms, rng_cnt = ktimes["spend_range"]
+    per_launch_proofs = n * K / max(rng_cnt, 1)
+    achieved = LIMB_MACS_PER_SPEND_RANGE * per_launch_proofs / (rng_ms / max(rng_cnt, 1) * 1e-3) if rng_ms else None
+    total_kernel_ms = sum(v[0] for v in ktimes.values())
+    hbm_bytes = n * K * (PROOF_BYTES + 128 + 161)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "int_mul", "kernel": "spend_range_kernel", "achieved": achieved / 1e12 if achieved else None, "peak": peak / 1e12,
+        "unit": "Tlimb-MAC/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+        "peak_source": "measured live: act_measure_int_mul_peak (independent IMAD.WIDE.U32 chains, 32x32+64->64)",
+        "work_per_unit": f"{LIMB_MACS_PER_SPEND_RANGE:.3g} limb-MACs per proof in this kernel (SURVEY 8d: 4.8e7 per spend, minus head/sign 1.4e6)",
+        "kernel_share_of_step": rng_ms / total_kernel_ms if total_kernel_ms else None,
+        "kernel_ms": {k: round(v[0], 3) for k, v in ktimes.items() if v[1]},
+        "whole_step": {"achieved": LIMB_MACS_PER_SPEND * n * K / (ms * 1e-3) / 1e12, "frac": LIMB_MACS_PER_SPEND * n * K / (ms * 1e-3) / peak},
+        "hbm": {"achieved_gbs": hbm_bytes / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "frac": hbm_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
+    }
+
+    # ---- issue (configs[1]) device-resident ----
+    d_req = torch.empty(ni * 128, dtype=torch.uint8, device=dev); d_cs = torch.empty(ni * 32, dtype=torch.uint8, device=dev)
+    d_irnd = torch.empty(ni * 128, dtype=torch.uint8, device=dev)
+    tile_to(d_req, reqs["req"], 128, ni, rank * 7); tile_to(d_cs, reqs["cs"], 32, ni, rank * 7); tile_to(d_irnd, reqs["rnd"], 128, ni, rank * 7)
+    d_resp = torch.zeros(ni * 160, dtype=torch.uint8, device=dev); d_ist = torch.zeros(ni, dtype=torch.uint8, device=dev)
+
+    def issue_step():
+        eng.batch_issue_dev(ni, d_req.data_ptr(), d_cs.data_ptr(), d_irnd.data_ptr(), d_resp.data_ptr(), d_ist.data_ptr(), stream)
+
+    ims = timed(issue_step, W, K)
+    assert (d_ist.cpu().numpy() == 0).all()
+    o_resp, o_ist, _ = ctx.batch_issue(np.roll(reqs["req"].reshape(-1, 128), -rank * 7, axis=0)[:8].reshape(-1).copy(),
+                                       np.roll(reqs["cs"].reshape(-1, 32), -rank * 7, axis=0)[:8].reshape(-1).copy(),
+                                       np.roll(reqs["rnd"].reshape(-1, 128), -rank * 7, axis=0)[:8].reshape(-1).copy(), threads=8)
+    assert (d_resp[:8 * 160].cpu().numpy() == o_resp).all(), "issue output differs from oracle"
+    issue_value = world * ni * K / (ims * 1e-3)
+
+    # ---- e2e: pinned host buffers through the public C ABI (H2D + kernels + D2H inside the timed region) ----
+    Ke = args.e2e_steps or K
+    del d_proofs, d_req
+    torch.cuda.empty_cache()
+    h_proofs = torch.empty(n * PROOF_BYTES, dtype=torch.uint8, pin_memory=True)
+    u = UNIQUE_PROOFS
+    hv = h_proofs.view(-1, PROOF_BYTES); src = torch.from_numpy(base["proofs"].reshape(u, PROOF_BYTES))
+    for off in range(0, n, u):
+        m = min(u, n - off); hv[off:off + m] = src[:m]
+    h_rnd = d_rnd.cpu().pin_memory()
+    h_ref = torch.empty(n * 128, dtype=torch.uint8, pin_memory=True); h_nul = torch.empty(n * 32, dtype=torch.uint8, pin_memory=True)
+    h_st = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+
+    def e2e_step():
+        eng.batch_verify_spend_and_refund_ptr(n, h_proofs.data_ptr(), h_rnd.data_ptr(), h_ref.data_ptr(), h_nul.data_ptr(), h_st.data_ptr())
+
+    e2e_step()  # warm-up (allocates the staging buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    assert (h_st.numpy() == 0).all()
+    e2e_value = world * n * Ke / e2e_s
+
+    hq = torch.from_numpy(np.tile(reqs["req"].reshape(-1, 128), ((ni + UNIQUE_REQUESTS - 1) // UNIQUE_REQUESTS, 1))[:ni].reshape(-1).copy()).pin_memory()
+    hc = d_cs.cpu().pin_memory(); hr = d_irnd.cpu().pin_memory()
+    hresp = torch.empty(ni * 160, dtype=torch.uint8, pin_memory=True); hst = torch.empty(ni, dtype=torch.uint8, pin_memory=True)
+
+    def e2e_issue():
+        eng.batch_issue_ptr(ni, hq.data_ptr(), hc.data_ptr(), hr.data_ptr(), hresp.data_ptr(), hst.data_ptr())
+
+    e2e_issue(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_issue()
+    barrier()
+    e2e_issue_s = time.perf_counter() - t0
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(ctx, base, reqs, os.cpu_count() or 1)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer)",
+            "data": "synthetic",
+            "config": {"workload": f"batch_verify_spend_and_refund of {n} SpendProofs per GPU (BASELINE configs[2]; x{world} GPUs = configs[3] shape), L=128, bench params",
+                       "unique_proofs": UNIQUE_PROOFS, "tiling": "valid proofs from the oracle prover tiled to the batch size",
+                       "l2": "inputs (17.6 GB per step) far larger than L2; no flush needed",
+                       "collective": "all_gather of status+nullifiers (33 B/proof) inside the step" if world > 1 else "none (single GPU)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (PROOF_BYTES + 128), "d2h_bytes_per_step": n * 161, "steps": Ke,
+                    "api": "act_batch_verify_spend_and_refund (C ABI, pinned host buffers)"},
+            "issue": {"metric": "issues_per_sec", "value": issue_value, "unit": "issues/s", "ms_per_step": ims / K, "n": ni,
+                      "workload": f"batch_issue of {ni} IssuanceRequests per GPU (BASELINE configs[1])",
+                      "e2e": {"value": world * ni * Ke / e2e_issue_s, "h2d_bytes_per_step": ni * 288, "d2h_bytes_per_step": ni * 161},
+                      "roofline_frac": LIMB_MACS_PER_ISSUE * issue_value / world / peak},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -113,6 +113,14 @@ ACT_API int act_batch_refund_check_dev(act_engine* e, size_t n, const void* com,
 /* Number of kernel launches issued by this engine since creation (for bench accounting). */
 ACT_API uint64_t act_engine_launch_count(const act_engine* e);
 
+/* Optional per-kernel device timing: when enabled every launch is bracketed by CUDA events on its stream.
+ * act_engine_get_timing sums and clears them per kernel kind: 0 spend_range, 1 spend_head, 2 spend_chunk (hash),
+ * 3 spend_finish, 4 refund_sign, 5 issue, 6 issuance_check, 7 refund_check. */
+ACT_API int act_engine_set_timing(act_engine* e, int enable);
+ACT_API int act_engine_get_timing(act_engine* e, double ms[8], uint64_t count[8]);
+/* Measured integer-multiply roofline of the device: sustained 32x32+64->64 multiply-adds per second. */
+ACT_API int act_measure_int_mul_peak(int device, double* limb_macs_per_s);
+
 /* Device self-test of the arithmetic layers against built-in known answers; 0 = pass. */
 ACT_API int act_selftest(int device);
 
