@@ -225,7 +225,7 @@ ACT_FN fe fe_reduce512(const u32* r) {
     return fe_fold9(t);
 }
 
-ACT_FN fe fe_mul(const fe& a, const fe& b) {
+ACT_FN fe fe_mul_inl(const fe& a, const fe& b) {
     u32 r[16];
 #if ACT_PTX
     u32 ev[18], od[18];
@@ -268,7 +268,189 @@ ACT_FN fe fe_mul(const fe& a, const fe& b) {
     return fe_reduce512(r);
 }
 
-ACT_FN fe fe_sq(const fe& a) { return fe_mul(a, a); }
+#if ACT_PTX
+// ---- GENERATED by tools/gen_fe_sq.py (layout verified there against big-int squaring) ----
+// 28 off-diagonal products in even/odd carry chains, doubled, plus the 8 diagonal squares: 36 wide
+// multiply-adds instead of 64.
+ACT_FN void fe_sq_wide(u32* r, const fe& a) {
+    u32 ev[16], od[16];
+    ACT_UNROLL for (int i = 0; i < 16; i++) { ev[i] = 0; od[i] = 0; }
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %9, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]));
+    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]), "+r"(ev[8])
+        : "r"(a.v[0]), "r"(a.v[2]), "r"(a.v[4]), "r"(a.v[6]));
+    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8])
+        : "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[4]), "r"(a.v[6]));
+    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]), "+r"(ev[8]), "+r"(ev[9]), "+r"(ev[10])
+        : "r"(a.v[1]), "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]));
+    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "+r"(od[9]), "+r"(od[10])
+        : "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(ev[6]), "+r"(ev[7]), "+r"(ev[8]), "+r"(ev[9]), "+r"(ev[10])
+        : "r"(a.v[2]), "r"(a.v[4]), "r"(a.v[6]));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "+r"(od[9]), "+r"(od[10])
+        : "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[6]));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(ev[8]), "+r"(ev[9]), "+r"(ev[10]), "+r"(ev[11]), "+r"(ev[12])
+        : "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(od[8]), "+r"(od[9]), "+r"(od[10]), "+r"(od[11]), "+r"(od[12])
+        : "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[7]));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(ev[10]), "+r"(ev[11]), "+r"(ev[12])
+        : "r"(a.v[4]), "r"(a.v[6]));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(od[10]), "+r"(od[11]), "+r"(od[12])
+        : "r"(a.v[5]), "r"(a.v[6]));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(ev[12]), "+r"(ev[13]), "+r"(ev[14])
+        : "r"(a.v[5]), "r"(a.v[7]));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(od[12]), "+r"(od[13]), "+r"(od[14])
+        : "r"(a.v[6]), "r"(a.v[7]));
+    ACT_UNROLL for (int i = 0; i < 16; i++) r[i] = ev[i];
+    asm("add.cc.u32 %0, %0, %15;\n\t"
+        "addc.cc.u32 %1, %1, %16;\n\t"
+        "addc.cc.u32 %2, %2, %17;\n\t"
+        "addc.cc.u32 %3, %3, %18;\n\t"
+        "addc.cc.u32 %4, %4, %19;\n\t"
+        "addc.cc.u32 %5, %5, %20;\n\t"
+        "addc.cc.u32 %6, %6, %21;\n\t"
+        "addc.cc.u32 %7, %7, %22;\n\t"
+        "addc.cc.u32 %8, %8, %23;\n\t"
+        "addc.cc.u32 %9, %9, %24;\n\t"
+        "addc.cc.u32 %10, %10, %25;\n\t"
+        "addc.cc.u32 %11, %11, %26;\n\t"
+        "addc.cc.u32 %12, %12, %27;\n\t"
+        "addc.cc.u32 %13, %13, %28;\n\t"
+        "addc.u32 %14, %14, %29;"
+        : "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+    asm("add.cc.u32 %0, %0, %0;\n\t"
+        "addc.cc.u32 %1, %1, %1;\n\t"
+        "addc.cc.u32 %2, %2, %2;\n\t"
+        "addc.cc.u32 %3, %3, %3;\n\t"
+        "addc.cc.u32 %4, %4, %4;\n\t"
+        "addc.cc.u32 %5, %5, %5;\n\t"
+        "addc.cc.u32 %6, %6, %6;\n\t"
+        "addc.cc.u32 %7, %7, %7;\n\t"
+        "addc.cc.u32 %8, %8, %8;\n\t"
+        "addc.cc.u32 %9, %9, %9;\n\t"
+        "addc.cc.u32 %10, %10, %10;\n\t"
+        "addc.cc.u32 %11, %11, %11;\n\t"
+        "addc.cc.u32 %12, %12, %12;\n\t"
+        "addc.cc.u32 %13, %13, %13;\n\t"
+        "addc.cc.u32 %14, %14, %14;\n\t"
+        "addc.u32 %15, %15, %15;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+}
+
+// ---- end GENERATED ----
+#endif
+
+ACT_FN fe fe_sq_inl(const fe& a) {
+#if ACT_PTX
+    u32 r[16];
+    fe_sq_wide(r, a);
+    return fe_reduce512(r);
+#else
+    return fe_mul_inl(a, a);
+#endif
+}
+// The multiply and the square are REAL calls (arguments and result travel in registers, checked in
+// SASS: no stack traffic).  Inlining them everywhere made spend_range_kernel 460 KB of code and ncu
+// showed the warps stalled on instruction fetch (stall_no_instruction 7.3 of 11.7 cycles per issue);
+// as calls the whole hot loop fits the instruction cache.
+#ifndef ACT_FE_CALLS
+#define ACT_FE_CALLS 1
+#endif
+#if ACT_FE_CALLS
+ACT_NOINLINE fe fe_mul(fe a, fe b) { return fe_mul_inl(a, b); }
+ACT_NOINLINE fe fe_sq(fe a) { return fe_sq_inl(a); }
+#else
+ACT_FN fe fe_mul(const fe& a, const fe& b) { return fe_mul_inl(a, b); }
+ACT_FN fe fe_sq(const fe& a) { return fe_sq_inl(a); }
+#endif
 
 ACT_FN fe fe_sqn(fe a, int n) {
     ACT_NOUNROLL for (int i = 0; i < n; i++) a = fe_sq(a);
