@@ -1,0 +1,67 @@
+"""Request-level sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+The hot path has no cross-request arithmetic (the reference's issue/refund take &self and are pure,
+/root/reference src/lib.rs:621,781), so a batch shards by contiguous index range with NO data-path
+collective.  The only exchange is the gather of per-request status bytes and 32-byte nullifiers
+(33 B / proof) so that every rank -- or the caller's nullifier database (src/lib.rs:741-745) -- sees the
+whole batch's accept bits.  Works with NCCL on GPU tensors and with gloo on CPU tensors (tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous range [lo, hi) of request indices owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_results(status, nullifiers, n_total, group=None):
+    """All-gather the per-shard status (uint8[m]) and nullifiers (uint8[m*32]) into whole-batch tensors
+    ordered by request index.  Shards may be ragged (shard_bounds)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return status, nullifiers
+    sizes = [shard_bounds(n_total, r, world) for r in range(world)]
+    mmax = max(hi - lo for lo, hi in sizes)
+    pad_s = torch.zeros(mmax, dtype=torch.uint8, device=status.device); pad_s[:status.numel()] = status
+    pad_n = torch.zeros(mmax * 32, dtype=torch.uint8, device=status.device); pad_n[:nullifiers.numel()] = nullifiers
+    out_s = torch.empty(world * mmax, dtype=torch.uint8, device=status.device)
+    out_n = torch.empty(world * mmax * 32, dtype=torch.uint8, device=status.device)
+    dist.all_gather_into_tensor(out_s, pad_s, group=group)
+    dist.all_gather_into_tensor(out_n, pad_n, group=group)
+    if all(hi - lo == mmax for lo, hi in sizes):
+        return out_s, out_n
+    s = torch.cat([out_s[r * mmax:r * mmax + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+    nl = torch.cat([out_n[r * mmax * 32:(r * mmax + (hi - lo)) * 32] for r, (lo, hi) in enumerate(sizes)])
+    return s, nl
+
+
+def flag_replays(status, nullifiers, seen=None):
+    """Caller-side double-spend screen over a gathered batch (the reference leaves this to the caller:
+    src/lib.rs:741-745, examples/act.rs:65-69, src/tests.rs:28-50).  Among ACCEPTED proofs (status 0) the first
+    occurrence of a nullifier in slice order keeps status 0; later ones -- and any nullifier present in `seen`
+    (uint8[k*32] of previously spent nullifiers) -- are flagged 3 (DoubleSpendError).  Refund outputs are not
+    touched.  Returns a new status tensor."""
+    n = status.numel()
+    if n == 0:
+        return status.clone()
+    keys = nullifiers.view(n, 32).contiguous().view(torch.int64).view(n, 4)
+    ok = status == 0
+    if seen is not None and seen.numel():
+        k = seen.numel() // 32
+        allk = torch.cat([seen.view(k, 32).contiguous().view(torch.int64).view(k, 4), keys])
+        first_pos = torch.cat([torch.full((k,), -1, dtype=torch.int64, device=status.device),
+                               torch.where(ok, torch.arange(n, device=status.device), torch.full((n,), n, device=status.device))])
+    else:
+        allk = keys
+        first_pos = torch.where(ok, torch.arange(n, device=status.device), torch.full((n,), n, device=status.device))
+    _, inv = torch.unique(allk, dim=0, return_inverse=True)
+    groups = int(inv.max().item()) + 1
+    first = torch.full((groups,), n, dtype=torch.int64, device=status.device).scatter_reduce(0, inv, first_pos, reduce="amin")
+    mine = inv[-n:]
+    dup = ok & (first[mine] != torch.arange(n, device=status.device))
+    out = status.clone()
+    out[dup] = 3
+    return out

@@ -1,0 +1,101 @@
+"""The C-ABI library loads and exports every symbol include/act_engine.h declares; host-only entry points (CBOR) work;
+compute entry points fail loudly without a GPU.  No compute calls here."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import corpus
+import refstack as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_all_declared_symbols(act):
+    hdr = open(os.path.join(ROOT, "include", "act_engine.h")).read()
+    declared = set(re.findall(r"ACT_API [^;(]*?\b(act_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = act.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(act.EXPORTED_SYMBOLS)
+
+
+def test_no_cpu_fallback(act):
+    if act.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(act.ActError):
+        act.Engine(act.Params(bytes(96)), act.PrivateKey(bytes(32), bytes(32)))
+    with pytest.raises(act.ActError):
+        act.Params.new("a", "b", "c", "d")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "anonymous-credit-tokens_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle_lib" not in src and "act_oracle" not in src and "hostsim" not in src.replace("tests/hostsim", ""), f
+
+
+def _golden():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "trip.json")))
+
+
+def test_cbor_encode_matches_reference_format(act):
+    g = _golden()
+    assert act.encode_issuance_request_cbor(bytes.fromhex(g["request"])).hex() == g["cbor_request"]
+    assert act.encode_issuance_response_cbor(bytes.fromhex(g["response"])).hex() == g["cbor_response"]
+    assert act.encode_refund_cbor(bytes.fromhex(g["refund"])).hex() == g["cbor_refund"]
+    import hashlib
+    enc = act.encode_spend_proof_cbor(bytes.fromhex(g["proof"]))
+    assert len(enc) == 18036 and enc[:4].hex() == "b1015820"
+    assert hashlib.sha256(enc).hexdigest() == g["cbor_proof_sha256"]
+
+
+def test_cbor_pack_roundtrip_and_lenient_rules(act):
+    import cbor2
+    g = _golden()
+    proof = bytes.fromhex(g["proof"]); req = bytes.fromhex(g["request"])
+    enc = act.encode_spend_proof_cbor(proof)
+    rec, st = act.pack_spend_proofs_cbor([enc, enc + b"trailing"])
+    assert st.tolist() == [0, 0] and rec[:16832].tobytes() == proof and rec[16832:].tobytes() == proof
+    f = lambda i: proof[32 * i:32 * i + 32]
+    good = {1: f(0), 2: f(1), 3: f(2), 4: f(3), 5: [f(4 + j) for j in range(128)], 6: f(132), 7: f(133), 8: f(134), 9: f(135), 10: f(136),
+            11: f(137), 12: f(138), 13: f(139), 14: [f(140 + j) for j in range(128)], 15: [[f(268 + 2 * j), f(269 + 2 * j)] for j in range(128)],
+            16: f(524), 17: f(525)}
+    assert cbor2.dumps(good) == enc
+    cases = []
+    # reordered keys + unknown keys + duplicate (last wins): still Ok (src/cbor.rs:299-383)
+    items = list(good.items())[::-1] + [(99, b"x"), ("str", 5)]
+    cases.append((cbor2.dumps(dict(items)), 0))
+    d = dict(good); d[5] = d[5][:127]; cases.append((cbor2.dumps(d), 0x82))           # Com array wrong size
+    d = dict(good); d[14] = d[14] + [f(0)]; cases.append((cbor2.dumps(d), 0x82))      # gamma0 array wrong size
+    d = dict(good); d[15] = [[a] for a, b in d[15]]; cases.append((cbor2.dumps(d), 0x82))   # z pair wrong size
+    d = dict(good); d[15] = [a for a, b in d[15]]; cases.append((cbor2.dumps(d), 0x82))     # expected array for z pair
+    d = dict(good); d[5] = b"notarray"; cases.append((cbor2.dumps(d), 0x82))          # non-array silently skipped -> missing field 5
+    d = dict(good); del d[17]; cases.append((cbor2.dumps(d), 0x82))                   # missing field
+    d = dict(good); d[6] = f(132)[:31]; cases.append((cbor2.dumps(d), 0x82))          # 31-byte scalar
+    d = dict(good); d[3] = 7; cases.append((cbor2.dumps(d), 0x82))                    # not bytes
+    cases.append((cbor2.dumps([1, 2, 3]), 0x82))                                      # not a map
+    cases.append((enc[:1000], 0x83))                                                  # truncated
+    cases.append((b"", 0x83))
+    cases.append((b"\xff", 0x83))
+    rec, st = act.pack_spend_proofs_cbor([c for c, _ in cases])
+    assert st.tolist() == [e for _, e in cases]
+    assert rec[:16832].tobytes() == proof
+    assert not rec[16832:2 * 16832].any()
+    # indefinite-length map and array, non-minimal integer keys
+    ind = b"\xbf" + b"".join(bytes([0x18, k]) + cbor2.dumps(v) for k, v in good.items() if k != 5) + b"\x05\x9f" + b"".join(cbor2.dumps(v) for v in good[5]) + b"\xff\xff"
+    rec, st = act.pack_spend_proofs_cbor([ind])
+    assert st.tolist() == [0] and rec.tobytes() == proof
+    # flat messages
+    rec, st = act.pack_issuance_requests_cbor([bytes.fromhex(g["cbor_request"]), cbor2.dumps({1: req[:32], 2: req[32:64], 3: req[64:96]})])
+    assert st.tolist() == [0, 0x82] and rec[:128].tobytes() == req
+    rec, st = act.pack_refunds_cbor([bytes.fromhex(g["cbor_refund"])])
+    assert st.tolist() == [0] and rec.tobytes().hex() == g["refund"]
+    rec, st = act.pack_issuance_responses_cbor([bytes.fromhex(g["cbor_response"])])
+    assert st.tolist() == [0] and rec.tobytes().hex() == g["response"]

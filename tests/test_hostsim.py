@@ -1,0 +1,127 @@
+"""The CUDA engine's device headers compiled for the host (tests/hostsim) vs the oracle: same per-thread kernel
+bodies, portable arithmetic paths.  Covers the engine's LOGIC without a GPU; the PTX paths and the launch plumbing
+are covered by the -m gpu tests."""
+import os
+import random
+
+import numpy as np
+
+import corpus
+import hostsim_lib as HS
+import oracle_lib as O
+
+ELL = corpus.ELL
+P = corpus.P25519
+b32 = lambda v: v.to_bytes(32, "little")
+
+
+def test_field_arithmetic_loose_inputs():
+    rnd = random.Random(1)
+    edge = [0, 1, 19, 38, P - 1, P, P + 1, 2 * P - 1, 2 * P, 2 * P + 37, 2**255 - 1, 2**255, 2**256 - 1, 2**256 - 38, 2**256 - 39]
+    vals = edge + [rnd.getrandbits(256) for _ in range(60)]
+    for a in vals:
+        for b in vals[::5]:
+            assert int.from_bytes(HS.call1("hs_fe_mul", b32(a), b32(b)), "little") == a * b % P
+            keep = [HS._in(b32(a)), HS._in(b32(b))]
+            s, sp = HS._out(32); d, dp = HS._out(32)
+            HS.lib().hs_fe_addsub(keep[0][1], keep[1][1], sp, dp)
+            assert int.from_bytes(s.tobytes(), "little") == (a + b) % P
+            assert int.from_bytes(d.tobytes(), "little") == (a - b) % P
+        if a % P:
+            assert int.from_bytes(HS.call1("hs_fe_invert", b32(a)), "little") == pow(a, -1, P)
+
+
+def test_scalar_arithmetic():
+    rnd = random.Random(2)
+    for it in range(100):
+        x, y, z = (rnd.getrandbits(256) for _ in range(3))
+        if it == 0:
+            x, y, z = 2**256 - 1, 2**256 - 1, 2**256 - 1
+        if it == 1:
+            x, y, z = 0, ELL, ELL - 1
+        assert int.from_bytes(HS.call1("hs_sc_reduce32", b32(x)), "little") == x % ELL
+        w = rnd.getrandbits(512) if it else 2**512 - 1
+        assert int.from_bytes(HS.call1("hs_sc_reduce64", w.to_bytes(64, "little")), "little") == w % ELL
+        assert int.from_bytes(HS.call1("hs_sc_muladd", b32(x), b32(y), b32(z)), "little") == (x * y + z) % ELL
+        inv = int.from_bytes(HS.call1("hs_sc_invert", b32(x)), "little")
+        assert inv == (pow(x % ELL, -1, ELL) if x % ELL else 0)
+        keep = [HS._in(b32(x)), HS._in(b32(y))]
+        n, np_ = HS._out(32); d, dp = HS._out(32)
+        HS.lib().hs_sc_negsub(keep[0][1], keep[1][1], np_, dp)
+        assert int.from_bytes(n.tobytes(), "little") == (-x) % ELL and int.from_bytes(d.tobytes(), "little") == (x - y) % ELL
+        # signed window recoding reconstructs the scalar
+        for wbits, nd in ((4, 64), (8, 32)):
+            a, ap = HS._in(b32(x)); dg = np.zeros(64, np.int8)
+            HS.lib().hs_recode(ap, wbits, dg.ctypes.data)
+            assert sum(int(dg[i]) << (wbits * i) for i in range(nd)) == x % ELL
+            assert all(-(1 << (wbits - 1)) <= int(v) < (1 << (wbits - 1)) for v in dg[:nd])
+
+
+def test_ristretto_codec_and_mults(octx):
+    rnd = random.Random(4)
+    hs = HS.Ctx(octx.h, octx.x, octx.w)
+    for b in corpus.bad_point_encodings():
+        a, ap = HS._in(b); o, op = HS._out(32)
+        assert HS.lib().hs_decode_encode(ap, op) == 0
+    for it in range(12):
+        u = bytes(rnd.getrandbits(8) for _ in range(64))
+        Pt = O.from_uniform(u)
+        assert HS.call1("hs_from_uniform", u) == Pt
+        a, ap = HS._in(Pt); o, op = HS._out(32)
+        assert HS.lib().hs_decode_encode(ap, op) == 1 and o.tobytes() == Pt
+        s = b32(rnd.getrandbits(256) % ELL if it else ELL - 1)
+        for ct in (0, 1):
+            k, kp = HS._in(s); o, op = HS._out(32)
+            assert HS.lib().hs_scalarmult(kp, ap, ct, op) == 1 and o.tobytes() == O.scalarmult(s, Pt)
+        assert hs.scalarmult_base(0, s, ct=0) == O.scalarmult_base(s) == hs.scalarmult_base(0, s, ct=1)
+        for base in (1, 2, 3):
+            assert hs.scalarmult_base(base, s) == O.scalarmult(s, octx.h[32 * (base - 1):32 * base])
+    z = bytes(32)
+    assert hs.scalarmult_base(0, z) == z and hs.scalarmult_base(0, z, ct=1) == z    # identity
+    assert hs.public_key(octx.x) == octx.w
+
+
+def test_blake3_single_chunk():
+    rnd = random.Random(6)
+    for n in [0, 1, 63, 64, 65, 186, 266, 425, 466, 1000, 1023, 1024]:
+        data = bytes(rnd.getrandbits(8) for _ in range(n))
+        a, ap = HS._in(data) if n else (None, None)
+        o, op = HS._out(64)
+        HS.lib().hs_blake3_small(ap, n, op)
+        assert o.tobytes() == O.blake3(data, 64)
+
+
+def test_params_derive():
+    for p in (corpus.TEST_PARAMS, corpus.BENCH_PARAMS, ("o", "s", "d", "v" * 300)):
+        assert HS.params_derive(*p) == O.params_derive(*p)
+
+
+def test_issue_refund_parity_with_mutations(octx):
+    hs = HS.Ctx(octx.h, octx.x, octx.w)
+    base = corpus.gen_valid(octx, 24, seed=b"hostsim", threads=8)
+    req, cs, rnd, expect, labels = corpus.mutate_requests(octx, base)
+    resp, st = hs.issue(req, cs, rnd)
+    o_resp, o_st, _ = octx.batch_issue(req, cs, rnd, threads=8)
+    assert st.tolist() == o_st.tolist() and (resp == o_resp).all()
+    K = base["req"].reshape(-1, 128)[:, :32].copy().reshape(-1)
+    r2 = base["resp"].reshape(-1, 160).copy()
+    r2[1, 32:64] = 0; r2[2, 96:97] ^= 1
+    st = hs.issuance_check(K, r2.reshape(-1)); o_st, _ = octx.batch_issuance_check(K, r2.reshape(-1), threads=8)
+    assert st.tolist() == o_st.tolist() and st[0] == 0 and st[1] == 2 and st[2] == 2
+    proofs, rnd, expect, labels = corpus.mutate_proofs(octx, base)
+    ref, nul, st = hs.refund(proofs, rnd)
+    o_ref, o_nul, o_st, _ = octx.batch_refund(proofs, rnd, threads=8)
+    assert st.tolist() == o_st.tolist() and (ref == o_ref).all() and (nul == o_nul).all()
+    com = proofs.reshape(-1, corpus.PROOF_BYTES)[:, 128:128 + 4096].copy().reshape(-1)
+    ref2 = ref.reshape(-1, 128).copy(); ref2[0, 64] ^= 1
+    st2 = hs.refund_check(com, ref2.reshape(-1)); o_st2, _ = octx.batch_refund_check(com, ref2.reshape(-1), threads=8)
+    assert st2.tolist() == o_st2.tolist() and st2[0] == 4
+
+
+def test_golden_corpus_small():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corpus_small.npz"))
+    hs = HS.Ctx(g["h"].tobytes(), g["x"].tobytes(), g["w"].tobytes())
+    resp, st = hs.issue(g["req"], g["cs"], g["rnd_issue"])
+    assert (st == g["status_issue"]).all() and (resp == g["resp"]).all()
+    ref, nul, st = hs.refund(g["proofs"], g["rnd"])
+    assert (st == g["status"]).all() and (ref == g["refunds"]).all() and (nul == g["nullifiers"]).all()
