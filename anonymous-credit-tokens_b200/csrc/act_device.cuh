@@ -94,6 +94,16 @@ ACT_FN void store8(u32* p, const u32* w) {
     for (int i = 0; i < 8; i++) p[i] = w[i];
 #endif
 }
+// plain (coherent) 32-byte load: for scratch written earlier by the same kernel (never __ldg there)
+ACT_FN void load8_rw(u32* w, const u32* p) {
+#if ACT_PTX
+    uint4 a = reinterpret_cast<const uint4*>(p)[0];
+    uint4 b = reinterpret_cast<const uint4*>(p)[1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) w[i] = p[i];
+#endif
+}
 ACT_FN void store8_zero(u32* p) {
     u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     store8(p, z);
@@ -144,22 +154,37 @@ ACT_FN ge fb_accumulate_ct(ge acc, const ge_niels* tab, const sc& s) {
 }
 
 // ---- variable-base: signed radix-16 windows over a per-thread table of 0..8 multiples -------------------
-struct vb_table { ge_cached e[9]; };
+// One entry = 128 contiguous bytes = one cache line, moved with 16-byte vector accesses.  (As a plain
+// per-thread array in local memory the divergent lookups fetched a 32-byte sector for every 4 bytes
+// used -- ncu: 1.6 B/sector, 8 MB of DRAM reads per proof -- so the range kernel keeps its tables in a
+// global scratch buffer instead; the small kernels keep them on the stack through the same accessors.)
+struct alignas(16) vb_table { ge_cached e[9]; };
 
+ACT_FN void tab_store(vb_table* t, u32 idx, const ge_cached& c) {
+    u32* q = reinterpret_cast<u32*>(&t->e[idx]);
+    store8(q, c.YpX.v); store8(q + 8, c.YmX.v); store8(q + 16, c.Z.v); store8(q + 24, c.T2d.v);
+}
+ACT_FN ge_cached tab_load(const vb_table* t, u32 idx) {
+    ge_cached c;
+    const u32* q = reinterpret_cast<const u32*>(&t->e[idx]);
+    load8_rw(c.YpX.v, q); load8_rw(c.YmX.v, q + 8); load8_rw(c.Z.v, q + 16); load8_rw(c.T2d.v, q + 24);
+    return c;
+}
 ACT_FN void vb_table_build(vb_table* t, const ge& P) {
-    t->e[0] = ge_cached_identity();
-    t->e[1] = ge_to_cached(P);
+    ge_cached c1 = ge_to_cached(P);
+    tab_store(t, 0, ge_cached_identity());
+    tab_store(t, 1, c1);
     ge Q = P;
     ACT_NOUNROLL for (int k = 2; k <= 8; k++) {
-        Q = ge_add_cached(Q, t->e[1]);
-        t->e[k] = ge_to_cached(Q);
+        Q = ge_add_cached(Q, c1);
+        tab_store(t, k, ge_to_cached(Q));
     }
 }
 ACT_FN ge_cached vb_lookup(const vb_table* t, int d, bool negate) {
     u32 neg = (d < 0) ? 1u : 0u;
     u32 idx = (u32)(d < 0 ? -d : d);
     if (negate) neg ^= 1u;
-    return ge_cached_cneg(t->e[idx], neg);
+    return ge_cached_cneg(tab_load(t, idx), neg);
 }
 ACT_FN ge_cached vb_lookup_ct(const vb_table* t, int d) {
     u32 neg = ((u32)d) >> 31;
@@ -167,8 +192,9 @@ ACT_FN ge_cached vb_lookup_ct(const vb_table* t, int d) {
     ge_cached e = ge_cached_identity();
     ACT_NOUNROLL for (u32 k = 1; k <= 8; k++) {
         u32 hit = (idx == k);
-        e.YpX = fe_select(e.YpX, t->e[k].YpX, hit); e.YmX = fe_select(e.YmX, t->e[k].YmX, hit);
-        e.Z = fe_select(e.Z, t->e[k].Z, hit); e.T2d = fe_select(e.T2d, t->e[k].T2d, hit);
+        ge_cached c = tab_load(t, k);
+        e.YpX = fe_select(e.YpX, c.YpX, hit); e.YmX = fe_select(e.YmX, c.YmX, hit);
+        e.Z = fe_select(e.Z, c.Z, hit); e.T2d = fe_select(e.T2d, c.T2d, hit);
     }
     return ge_cached_cneg(e, neg);
 }
@@ -193,9 +219,8 @@ ACT_FN ge vb_mul(const vb_table* t, const sc& s, bool negate) { return vb_mul_mu
 // each scalar costs only 256/M doublings:  s*P = sum_k 2^(256k/M) * (sum_i 16^i d_{k*WIN+i}) P.
 // Q0 = -s0*P, Q1 = -s1*P.   M = 4: 192 + 2*64 doublings instead of 2*256.
 template <int M>
-ACT_FN void vb_mul_dual_split(const ge& P, const sc& s0, const sc& s1, ge* Q0, ge* Q1) {
+ACT_FN void vb_mul_dual_split(const ge& P, const sc& s0, const sc& s1, ge* Q0, ge* Q1, vb_table* t /* M tables of scratch */) {
     const int WIN = 64 / M;
-    vb_table t[M];
     {
         ge Q = P;
         ACT_NOUNROLL for (int k = 0; k < M; k++) {
@@ -387,7 +412,8 @@ ACT_FN void issuance_check_thread(const act_ctx* C, size_t i, const u32* Kin, co
 // One thread per (proof, j).  Writes items 5+j (com_j bytes), 133+2j, 134+2j (C'_j0, C'_j1) and the
 // affine-Niels form of com_j for the K' Horner chain in stage 2.
 // =============================================================================================================
-ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* proofs, u32* items, u32* com_niels, u32* flags) {
+ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* proofs, u32* items, u32* com_niels, u32* flags,
+                               vb_table* tabs /* ACT_RANGE_SPLIT tables private to this thread */) {
     const u32* pf = proofs + (size_t)ACT_PROOF_WORDS * p;
     u32* it = items + (size_t)ACT_ITEM_WORDS * p;
     u32 cw[8];
@@ -406,7 +432,7 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
     sc g1 = sc_sub(gamma, g0);                                                             // gamma01[j]  (:801,811)
     sc z0 = load_scalar(pf + 8 * (268 + 2 * j)), z1 = load_scalar(pf + 8 * (269 + 2 * j));
     ge Q0, Q1;
-    vb_mul_dual_split<ACT_RANGE_SPLIT>(P, g0, g1, &Q0, &Q1);   // -com_j*gamma0_j, -com_j*gamma01_j
+    vb_mul_dual_split<ACT_RANGE_SPLIT>(P, g0, g1, &Q0, &Q1, tabs);   // -com_j*gamma0_j, -com_j*gamma01_j
     // C'_j0 = [h2*w00 +] h3*z_j0 - com_j*gamma0_j                                          (:806-807,814-815)
     Q0 = fb_accumulate(Q0, C->fb[ACT_BASE_H3], z0, false);
     if (j == 0) Q0 = fb_accumulate(Q0, C->fb[ACT_BASE_H2], load_scalar(pf + 8 * 138), false);

@@ -32,9 +32,13 @@ __global__ void __launch_bounds__(ACT_ISSUE_BLOCK) issuance_check_kernel(const a
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issuance_check_thread(C, i, K, resp, status);
 }
-// one block of 128 threads per proof: thread j owns com_j and the pair C'_j0, C'_j1
-__global__ void __launch_bounds__(ACT_L) spend_range_kernel(const act_ctx* C, const u32* proofs, u32* items, u32* com_niels, u32* flags) {
-    spend_range_thread(C, blockIdx.x, threadIdx.x, proofs, items, com_niels, flags);
+// One block of 128 threads works on one proof at a time: thread j owns com_j and the pair C'_j0, C'_j1.  The grid is
+// sized to the machine (SMs x resident blocks) and strides over the chunk, so the per-thread window tables live in a
+// scratch buffer indexed by (block, thread) that stays small enough to sit in L2 whatever the batch size.
+#define ACT_RANGE_BLOCKS_PER_SM 3
+__global__ void __launch_bounds__(ACT_L, ACT_RANGE_BLOCKS_PER_SM) spend_range_kernel(const act_ctx* C, size_t m, const u32* proofs, u32* items, u32* com_niels, u32* flags, vb_table* tabs) {
+    vb_table* mine = tabs + ((size_t)blockIdx.x * ACT_L + threadIdx.x) * ACT_RANGE_SPLIT;
+    for (size_t p = blockIdx.x; p < m; p += gridDim.x) spend_range_thread(C, p, threadIdx.x, proofs, items, com_niels, flags, mine);
 }
 __global__ void __launch_bounds__(ACT_HEAD_BLOCK) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,6 +168,8 @@ static int fail_msg(const char* what) { g_err = what; return -1; }
 
 struct spend_scratch {
     u32 *items = nullptr, *com_niels = nullptr, *kprime = nullptr, *flags = nullptr, *cvs = nullptr;
+    vb_table* tabs = nullptr;   // window tables of the range kernel: grid x 128 threads x ACT_RANGE_SPLIT
+    unsigned range_grid = 0;
     size_t cap = 0;
 };
 struct io_slot {  // device staging for the host-buffer entry points
@@ -206,6 +212,15 @@ static int ensure(u8** p, size_t* cap, size_t need) {
     return 0;
 }
 static int ensure_scratch(spend_scratch* s, size_t n) {
+    if (!s->tabs) {
+        int dev = 0, sms = 0, per_sm = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spend_range_kernel, ACT_L, 0));
+        if (per_sm < 1) per_sm = 1;
+        s->range_grid = (unsigned)(sms * per_sm);
+        CK(cudaMalloc((void**)&s->tabs, (size_t)s->range_grid * ACT_L * ACT_RANGE_SPLIT * sizeof(vb_table)));
+    }
     if (s->cap >= n) return 0;
     cudaFree(s->items); cudaFree(s->com_niels); cudaFree(s->kprime); cudaFree(s->flags); cudaFree(s->cvs);
     s->cap = 0;
@@ -271,7 +286,7 @@ extern "C" void act_engine_destroy(act_engine* e) {
     cudaFree(e->d_tables); cudaFree(e->d_bases);
     for (int s = 0; s < 2; s++) {
         spend_scratch& sc_ = e->scratch[s];
-        cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs);
+        cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs); cudaFree(sc_.tabs);
         io_slot& io = e->io[s];
         cudaFree(io.in0); cudaFree(io.in1); cudaFree(io.in2); cudaFree(io.out0); cudaFree(io.out1); cudaFree(io.st);
         if (e->stream[s]) cudaStreamDestroy(e->stream[s]);
@@ -477,7 +492,8 @@ extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* c
 static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, size_t m, const u32* proofs, const u32* rnd,
                               u32* refunds, u32* nullifiers, u8* status) {
     CK(cudaMemsetAsync(s->flags, 0, m * 4, st));
-    LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<(unsigned)m, ACT_L, 0, st>>>(e->d_ctx, proofs, s->items, s->com_niels, s->flags)));
+    unsigned rgrid = m < s->range_grid ? (unsigned)m : s->range_grid;
+    LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<rgrid, ACT_L, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->flags, s->tabs)));
     LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->kprime, s->flags)));
     LAUNCH(e, K_CHUNK, st, (spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, s->items, s->cvs)));
     LAUNCH(e, K_FINISH, st, (spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status)));

@@ -24,44 +24,71 @@ ACT_FN ge_cached ge_to_cached(const ge& p) {
 }
 ACT_FN ge ge_neg(const ge& p) { ge r; r.X = fe_neg(p.X); r.Y = p.Y; r.Z = p.Z; r.T = fe_neg(p.T); return r; }
 
-// r = p + q, 8M (+1M for T when want_t)
-ACT_FN ge ge_add_cached(const ge& p, const ge_cached& q) {
-    fe PP = fe_mul(fe_add(p.Y, p.X), q.YpX);
-    fe MM = fe_mul(fe_sub(p.Y, p.X), q.YmX);
-    fe TT = fe_mul(p.T, q.T2d);
-    fe ZZ = fe_mul(p.Z, q.Z);
+// The three hot point operations.  ACT_GE_CALLS=1 makes THEM the call boundary (field multiplies inlined inside:
+// one round of argument moves per 7-8 multiplies).  Measured on B200 it is slower (90k vs 119k proofs/s): the
+// three bodies together no longer fit the instruction cache.  Default 0 = calls at the field-multiply level.
+#ifndef ACT_GE_CALLS
+#define ACT_GE_CALLS 0
+#endif
+#if ACT_GE_CALLS
+#define ACT_GE_FN ACT_NOINLINE
+#define GE_MUL fe_mul_inl
+#define GE_SQ fe_sq_inl
+#else
+#define ACT_GE_FN ACT_FN
+#define GE_MUL fe_mul
+#define GE_SQ fe_sq
+#endif
+// r = p + q, 8M
+ACT_GE_FN ge ge_add_cached(ge p, ge_cached q) {
+    fe PP = GE_MUL(fe_add(p.Y, p.X), q.YpX);
+    fe MM = GE_MUL(fe_sub(p.Y, p.X), q.YmX);
+    fe TT = GE_MUL(p.T, q.T2d);
+    fe ZZ = GE_MUL(p.Z, q.Z);
     fe ZZ2 = fe_add(ZZ, ZZ);
     fe E = fe_sub(PP, MM), H = fe_add(PP, MM), G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
     ge r;
-    r.X = fe_mul(E, F); r.Y = fe_mul(H, G); r.Z = fe_mul(G, F); r.T = fe_mul(E, H);
+    r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
     return r;
 }
 // r = p + q for affine-Niels q, 7M
-ACT_FN ge ge_add_niels(const ge& p, const ge_niels& q) {
-    fe PP = fe_mul(fe_add(p.Y, p.X), q.ypx);
-    fe MM = fe_mul(fe_sub(p.Y, p.X), q.ymx);
-    fe TT = fe_mul(p.T, q.xy2d);
+ACT_GE_FN ge ge_add_niels(ge p, ge_niels q) {
+    fe PP = GE_MUL(fe_add(p.Y, p.X), q.ypx);
+    fe MM = GE_MUL(fe_sub(p.Y, p.X), q.ymx);
+    fe TT = GE_MUL(p.T, q.xy2d);
     fe ZZ2 = fe_add(p.Z, p.Z);
     fe E = fe_sub(PP, MM), H = fe_add(PP, MM), G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
     ge r;
-    r.X = fe_mul(E, F); r.Y = fe_mul(H, G); r.Z = fe_mul(G, F); r.T = fe_mul(E, H);
+    r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
     return r;
 }
 ACT_FN ge ge_add(const ge& p, const ge& q) { return ge_add_cached(p, ge_to_cached(q)); }
 ACT_FN ge ge_sub(const ge& p, const ge& q) { return ge_add_cached(p, ge_to_cached(ge_neg(q))); }
 
-// r = 2p.  T of the input is not read; T of the output is produced only when want_t (4S + 3M / 4M).
-ACT_FN ge ge_dbl(const ge& p, bool want_t) {
-    fe XX = fe_sq(p.X), YY = fe_sq(p.Y), ZZ = fe_sq(p.Z);
+// r = 2p.  T of the input is not read (4S + 4M; the T product is computed unconditionally in the call form
+// so that a single instance of the code serves every doubling).
+ACT_GE_FN ge ge_dbl_t(ge p) {
+    fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y), ZZ = GE_SQ(p.Z);
     fe ZZ2 = fe_add(ZZ, ZZ);
-    fe XpY2 = fe_sq(fe_add(p.X, p.Y));
+    fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
     fe Yc = fe_add(YY, XX), Zc = fe_sub(YY, XX);
     fe Xc = fe_sub(XpY2, Yc), Tc = fe_sub(ZZ2, Zc);
     ge r;
-    r.X = fe_mul(Xc, Tc); r.Y = fe_mul(Yc, Zc); r.Z = fe_mul(Zc, Tc);
-    if (want_t) r.T = fe_mul(Xc, Yc); else r.T = fe_zero();
+    r.X = GE_MUL(Xc, Tc); r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Zc, Tc); r.T = GE_MUL(Xc, Yc);
     return r;
 }
+// doubling without the T output (4S + 3M): p.T is carried through untouched and must not be used
+ACT_GE_FN ge ge_dbl_not(ge p) {
+    fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y), ZZ = GE_SQ(p.Z);
+    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
+    fe Yc = fe_add(YY, XX), Zc = fe_sub(YY, XX);
+    fe Xc = fe_sub(XpY2, Yc), Tc = fe_sub(ZZ2, Zc);
+    ge r;
+    r.X = GE_MUL(Xc, Tc); r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Zc, Tc); r.T = p.T;
+    return r;
+}
+ACT_FN ge ge_dbl(const ge& p, bool want_t) { return want_t ? ge_dbl_t(p) : ge_dbl_not(p); }
 
 // branch-free negate-if of table entries (negation swaps y+x / y-x and flips the sign of the t term)
 ACT_FN ge_cached ge_cached_cneg(const ge_cached& q, u32 neg) {

@@ -100,8 +100,9 @@ EXPORT void hs_refund(const hs_ctx* H, size_t n, const uint8_t* proofs, const ui
     auto pf = to_words(proofs, n * (size_t)ACT_PROOF_WORDS * 4), d = to_words(rnd, n * 128);
     std::vector<u32> items(n * (size_t)ACT_ITEM_WORDS + 8), cn(n * (size_t)ACT_L * 24 + 8), kp(n * 32 + 8), flags(n + 1, 0),
         cvs(n * ACT_SPEND_CHUNKS * 8 + 8), ro(n * 32 + 8), no(n * 8 + 8);
+    std::vector<vb_table> tabs(ACT_RANGE_SPLIT);
     for (size_t p = 0; p < n; p++)
-        for (int j = 0; j < ACT_L; j++) spend_range_thread(&H->c, p, j, pf.data(), items.data(), cn.data(), flags.data());
+        for (int j = 0; j < ACT_L; j++) spend_range_thread(&H->c, p, j, pf.data(), items.data(), cn.data(), flags.data(), tabs.data());
     for (size_t p = 0; p < n; p++) spend_head_thread(&H->c, p, pf.data(), items.data(), cn.data(), kp.data(), flags.data());
     for (size_t p = 0; p < n; p++)
         for (int c = 0; c < ACT_SPEND_CHUNKS; c++) spend_chunk_thread(&H->c, p, c, items.data(), cvs.data());
