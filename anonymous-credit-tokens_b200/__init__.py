@@ -135,7 +135,7 @@ def selftest(device=0):
 
 
 KERNEL_KINDS = ["spend_range", "spend_head", "spend_chunk_hash", "spend_finish", "refund_sign", "issue",
-                "issuance_check", "refund_check"]
+                "issuance_check", "refund_check", "spend_encode"]
 
 
 def measure_int_mul_peak(device=0):
@@ -217,7 +217,7 @@ class Engine:
 
     def get_timing(self):
         """{kernel kind: (total device ms, launches)} since the last call (synchronises)."""
-        ms = (C.c_double * 8)(); cnt = (C.c_uint64 * 8)()
+        ms = (C.c_double * 9)(); cnt = (C.c_uint64 * 9)()
         _check(self.lib.act_engine_get_timing(self._h, C.addressof(ms), C.addressof(cnt)), "act_engine_get_timing")
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(KERNEL_KINDS)}
 

@@ -413,7 +413,7 @@ ACT_FN void issuance_check_thread(const act_ctx* C, size_t i, const u32* Kin, co
 // affine-Niels form of com_j for the K' Horner chain in stage 2.
 // =============================================================================================================
 ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* proofs, u32* items, u32* com_niels, u32* flags,
-                               vb_table* tabs /* ACT_RANGE_SPLIT tables private to this thread */) {
+                               vb_table* tabs /* ACT_RANGE_SPLIT tables private to this thread */, u32* cpts /* n x 256 x 32 words */) {
     const u32* pf = proofs + (size_t)ACT_PROOF_WORDS * p;
     u32* it = items + (size_t)ACT_ITEM_WORDS * p;
     u32 cw[8];
@@ -427,21 +427,63 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
         u32* cn = com_niels + ((size_t)ACT_L * p + j) * 24;
         store_fe(cn, n.ypx); store_fe(cn + 8, n.ymx); store_fe(cn + 16, n.xy2d);
     }
+    // Every scalar is HALVED: this stage produces C'/2 and the encode stage emits encode(2 * C'/2) with one batched
+    // inversion per 16 points instead of one inverse square root per point.
     sc gamma = load_scalar(pf + 8 * 132);
-    sc g0 = load_scalar(pf + 8 * (140 + j));
-    sc g1 = sc_sub(gamma, g0);                                                             // gamma01[j]  (:801,811)
-    sc z0 = load_scalar(pf + 8 * (268 + 2 * j)), z1 = load_scalar(pf + 8 * (269 + 2 * j));
+    sc g0f = load_scalar(pf + 8 * (140 + j));
+    sc g0 = sc_half(g0f);
+    sc g1 = sc_half(sc_sub(gamma, g0f));                                                    // gamma01[j] / 2  (:801,811)
+    sc z0 = sc_half(load_scalar(pf + 8 * (268 + 2 * j))), z1 = sc_half(load_scalar(pf + 8 * (269 + 2 * j)));
     ge Q0, Q1;
-    vb_mul_dual_split<ACT_RANGE_SPLIT>(P, g0, g1, &Q0, &Q1, tabs);   // -com_j*gamma0_j, -com_j*gamma01_j
+    vb_mul_dual_split<ACT_RANGE_SPLIT>(P, g0, g1, &Q0, &Q1, tabs);   // -com_j*gamma0_j/2, -com_j*gamma01_j/2
     // C'_j0 = [h2*w00 +] h3*z_j0 - com_j*gamma0_j                                          (:806-807,814-815)
     Q0 = fb_accumulate(Q0, C->fb[ACT_BASE_H3], z0, false);
-    if (j == 0) Q0 = fb_accumulate(Q0, C->fb[ACT_BASE_H2], load_scalar(pf + 8 * 138), false);
-    store_point(it + 8 * (133 + 2 * j), Q0);
+    if (j == 0) Q0 = fb_accumulate(Q0, C->fb[ACT_BASE_H2], sc_half(load_scalar(pf + 8 * 138)), false);
     // C'_j1 = [h2*w01 +] h3*z_j1 - (com_j - h1)*gamma01_j = ... + h1*gamma01_j - com_j*gamma01_j   (:808-809,816)
     Q1 = fb_accumulate(Q1, C->fb[ACT_BASE_H3], z1, false);
     Q1 = fb_accumulate(Q1, C->fb[ACT_BASE_H1], g1, false);
-    if (j == 0) Q1 = fb_accumulate(Q1, C->fb[ACT_BASE_H2], load_scalar(pf + 8 * 139), false);
-    store_point(it + 8 * (134 + 2 * j), Q1);
+    if (j == 0) Q1 = fb_accumulate(Q1, C->fb[ACT_BASE_H2], sc_half(load_scalar(pf + 8 * 139)), false);
+    u32* cp = cpts + ((size_t)2 * ACT_L * p + 2 * j) * 32;
+    store_fe(cp, Q0.X); store_fe(cp + 8, Q0.Y); store_fe(cp + 16, Q0.Z); store_fe(cp + 24, Q0.T);
+    store_fe(cp + 32, Q1.X); store_fe(cp + 40, Q1.Y); store_fe(cp + 48, Q1.Z); store_fe(cp + 56, Q1.T);
+}
+
+// =============================================================================================================
+// spend verification, stage 1b: encode the 256 half-commitments of a proof.  One thread per ACT_ENC_BATCH
+// consecutive points: Montgomery-batched inversion, then the square-root-free double-and-encode.
+// Writes items 133 .. 388.
+// =============================================================================================================
+#define ACT_ENC_BATCH 16
+ACT_FN void spend_encode_thread(const act_ctx* C, size_t p, int part, const u32* cpts, u32* items) {
+    (void)C;
+    const u32* src = cpts + ((size_t)2 * ACT_L * p + (size_t)part * ACT_ENC_BATCH) * 32;
+    u32* dst = items + (size_t)ACT_ITEM_WORDS * p + 8 * (133 + part * ACT_ENC_BATCH);
+    fe prefix[ACT_ENC_BATCH];
+    fe acc = fe_one();
+    ACT_NOUNROLL for (int i = 0; i < ACT_ENC_BATCH; i++) {
+        ge P;
+        load_fe(&P.X, src + 32 * i); load_fe(&P.Y, src + 32 * i + 8); load_fe(&P.Z, src + 32 * i + 16); load_fe(&P.T, src + 32 * i + 24);
+        ge_dbl_enc s = ge_dbl_enc_prepare(P);
+        fe t = fe_mul(s.eg, s.fh);
+        t = fe_select(t, fe_one(), fe_is_zero(t));
+        prefix[i] = acc;            // product of t_0 .. t_{i-1}
+        acc = fe_mul(acc, t);
+    }
+    fe inv = fe_invert(acc);
+    ACT_NOUNROLL for (int i = ACT_ENC_BATCH - 1; i >= 0; i--) {
+        ge P;
+        load_fe(&P.X, src + 32 * i); load_fe(&P.Y, src + 32 * i + 8); load_fe(&P.Z, src + 32 * i + 16); load_fe(&P.T, src + 32 * i + 24);
+        ge_dbl_enc s = ge_dbl_enc_prepare(P);
+        fe t = fe_mul(s.eg, s.fh);
+        u32 zero = fe_is_zero(t);
+        t = fe_select(t, fe_one(), zero);
+        fe inv_i = fe_mul(inv, prefix[i]);
+        inv = fe_mul(inv, t);
+        u32 w[8];
+        ge_dbl_enc_finish(w, s, inv_i);
+        ACT_UNROLL for (int k = 0; k < 8; k++) w[k] = zero ? 0u : w[k];   // 2P in the identity coset
+        store8(dst + 8 * i, w);
+    }
 }
 
 // =============================================================================================================

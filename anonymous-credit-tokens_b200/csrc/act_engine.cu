@@ -24,11 +24,11 @@
 #define ACT_SIGN_BLOCK 64
 #define ACT_HASH_BLOCK 128
 
-__global__ void __launch_bounds__(ACT_ISSUE_BLOCK) issue_kernel(const act_ctx* C, size_t n, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status) {
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issue_kernel(const act_ctx* C, size_t n, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issue_thread(C, i, req, cs, rnd, resp, status);
 }
-__global__ void __launch_bounds__(ACT_ISSUE_BLOCK) issuance_check_kernel(const act_ctx* C, size_t n, const u32* K, const u32* resp, u8* status) {
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issuance_check_kernel(const act_ctx* C, size_t n, const u32* K, const u32* resp, u8* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issuance_check_thread(C, i, K, resp, status);
 }
@@ -36,11 +36,18 @@ __global__ void __launch_bounds__(ACT_ISSUE_BLOCK) issuance_check_kernel(const a
 // sized to the machine (SMs x resident blocks) and strides over the chunk, so the per-thread window tables live in a
 // scratch buffer indexed by (block, thread) that stays small enough to sit in L2 whatever the batch size.
 #define ACT_RANGE_BLOCKS_PER_SM 3
-__global__ void __launch_bounds__(ACT_L, ACT_RANGE_BLOCKS_PER_SM) spend_range_kernel(const act_ctx* C, size_t m, const u32* proofs, u32* items, u32* com_niels, u32* flags, vb_table* tabs) {
+__global__ void __launch_bounds__(ACT_L, ACT_RANGE_BLOCKS_PER_SM) spend_range_kernel(const act_ctx* C, size_t m, const u32* proofs, u32* items, u32* com_niels, u32* flags, vb_table* tabs, u32* cpts) {
     vb_table* mine = tabs + ((size_t)blockIdx.x * ACT_L + threadIdx.x) * ACT_RANGE_SPLIT;
-    for (size_t p = blockIdx.x; p < m; p += gridDim.x) spend_range_thread(C, p, threadIdx.x, proofs, items, com_niels, flags, mine);
+    for (size_t p = blockIdx.x; p < m; p += gridDim.x) spend_range_thread(C, p, threadIdx.x, proofs, items, com_niels, flags, mine, cpts);
 }
-__global__ void __launch_bounds__(ACT_HEAD_BLOCK) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
+// encodes the 256 commitments of each proof: one thread per 16 points (batched inversion)
+#define ACT_ENC_BLOCK 128
+#define ACT_ENC_PARTS (2 * ACT_L / ACT_ENC_BATCH)
+__global__ void __launch_bounds__(ACT_ENC_BLOCK, 4) spend_encode_kernel(const act_ctx* C, size_t m, const u32* cpts, u32* items) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m * ACT_ENC_PARTS) spend_encode_thread(C, t / ACT_ENC_PARTS, (int)(t % ACT_ENC_PARTS), cpts, items);
+}
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK, 8) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) spend_head_thread(C, p, proofs, items, com_niels, kprime, flags);
 }
@@ -52,11 +59,11 @@ __global__ void __launch_bounds__(ACT_HASH_BLOCK) spend_finish_kernel(const act_
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) spend_finish_thread(C, p, proofs, cvs, flags, status);
 }
-__global__ void __launch_bounds__(ACT_SIGN_BLOCK) refund_sign_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* rnd, const u32* kprime, const u8* status, u32* refunds, u32* nullifiers) {
+__global__ void __launch_bounds__(ACT_SIGN_BLOCK, 8) refund_sign_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* rnd, const u32* kprime, const u8* status, u32* refunds, u32* nullifiers) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) refund_sign_thread(C, p, proofs, rnd, kprime, status, refunds, nullifiers);
 }
-__global__ void __launch_bounds__(ACT_HEAD_BLOCK) refund_check_kernel(const act_ctx* C, size_t n, const u32* com, const u32* refund, u8* status) {
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK, 8) refund_check_kernel(const act_ctx* C, size_t n, const u32* com, const u32* refund, u8* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) refund_check_thread(C, i, com, refund, status);
 }
@@ -168,6 +175,7 @@ static int fail_msg(const char* what) { g_err = what; return -1; }
 
 struct spend_scratch {
     u32 *items = nullptr, *com_niels = nullptr, *kprime = nullptr, *flags = nullptr, *cvs = nullptr;
+    u32* cpts = nullptr;        // half-commitments C'/2 in extended coordinates: m x 256 x 128 B
     vb_table* tabs = nullptr;   // window tables of the range kernel: grid x 128 threads x ACT_RANGE_SPLIT
     unsigned range_grid = 0;
     size_t cap = 0;
@@ -180,6 +188,7 @@ struct io_slot {  // device staging for the host-buffer entry points
 struct act_engine {
     int device = 0;
     cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
     act_ctx* d_ctx = nullptr;
     ge_niels* d_tables = nullptr;
     ge* d_bases = nullptr;
@@ -191,7 +200,7 @@ struct act_engine {
     struct timed { int kind; cudaEvent_t a, b; };
     std::vector<timed> events;
 };
-enum { K_RANGE = 0, K_HEAD, K_CHUNK, K_FINISH, K_SIGN, K_ISSUE, K_ISSUANCE_CHECK, K_REFUND_CHECK, K_KINDS };
+enum { K_RANGE = 0, K_HEAD, K_CHUNK, K_FINISH, K_SIGN, K_ISSUE, K_ISSUANCE_CHECK, K_REFUND_CHECK, K_ENCODE, K_KINDS };
 
 // LAUNCH(e, kind, stream, kernel<<<...>>>(...)) : counts the launch and, when timing is on, brackets it with events
 #define LAUNCH(e, kind, st, ...)                                                              \
@@ -222,8 +231,9 @@ static int ensure_scratch(spend_scratch* s, size_t n) {
         CK(cudaMalloc((void**)&s->tabs, (size_t)s->range_grid * ACT_L * ACT_RANGE_SPLIT * sizeof(vb_table)));
     }
     if (s->cap >= n) return 0;
-    cudaFree(s->items); cudaFree(s->com_niels); cudaFree(s->kprime); cudaFree(s->flags); cudaFree(s->cvs);
+    cudaFree(s->items); cudaFree(s->com_niels); cudaFree(s->kprime); cudaFree(s->flags); cudaFree(s->cvs); cudaFree(s->cpts);
     s->cap = 0;
+    CK(cudaMalloc((void**)&s->cpts, n * 2 * ACT_L * 128));
     CK(cudaMalloc((void**)&s->items, n * ACT_ITEM_WORDS * 4));
     CK(cudaMalloc((void**)&s->com_niels, n * ACT_L * 96));
     CK(cudaMalloc((void**)&s->kprime, n * 128));
@@ -284,9 +294,11 @@ extern "C" void act_engine_destroy(act_engine* e) {
     cudaDeviceSynchronize();
     if (e->d_ctx) { cudaMemset(e->d_ctx, 0, sizeof(act_ctx)); cudaFree(e->d_ctx); }  // zeroise x on the device
     cudaFree(e->d_tables); cudaFree(e->d_bases);
+    if (e->fork) cudaEventDestroy(e->fork);
+    for (int s = 0; s < 2; s++) if (e->join[s]) cudaEventDestroy(e->join[s]);
     for (int s = 0; s < 2; s++) {
         spend_scratch& sc_ = e->scratch[s];
-        cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs); cudaFree(sc_.tabs);
+        cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs); cudaFree(sc_.tabs); cudaFree(sc_.cpts);
         io_slot& io = e->io[s];
         cudaFree(io.in0); cudaFree(io.in1); cudaFree(io.in2); cudaFree(io.out0); cudaFree(io.out1); cudaFree(io.st);
         if (e->stream[s]) cudaStreamDestroy(e->stream[s]);
@@ -311,6 +323,9 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
 #define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
         CKB(cudaStreamCreateWithFlags(&e->stream[0], cudaStreamNonBlocking));
         CKB(cudaStreamCreateWithFlags(&e->stream[1], cudaStreamNonBlocking));
+        CKB(cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming));
+        CKB(cudaEventCreateWithFlags(&e->join[0], cudaEventDisableTiming));
+        CKB(cudaEventCreateWithFlags(&e->join[1], cudaEventDisableTiming));
         CKB(cudaMalloc((void**)&e->d_ctx, sizeof(act_ctx)));
         CKB(cudaMalloc((void**)&e->d_tables, sizeof(ge_niels) * (4 * (size_t)ACT_FB_SIZE + ACT_CT_SIZE)));
         CKB(cudaMalloc((void**)&e->d_bases, sizeof(ge) * 4));
@@ -385,8 +400,9 @@ extern "C" int act_engine_set_timing(act_engine* e, int enable) {
     return 0;
 }
 // Sums (and clears) the device time of every launch recorded since the last call, per kernel kind:
-// 0 spend_range, 1 spend_head, 2 spend_chunk(hash), 3 spend_finish, 4 refund_sign, 5 issue, 6 issuance_check, 7 refund_check.
-extern "C" int act_engine_get_timing(act_engine* e, double ms[8], uint64_t count[8]) {
+// 0 spend_range, 1 spend_head, 2 spend_chunk(hash), 3 spend_finish, 4 refund_sign, 5 issue, 6 issuance_check, 7 refund_check,
+// 8 spend_encode.
+extern "C" int act_engine_get_timing(act_engine* e, double ms[9], uint64_t count[9]) {
     if (!e || !ms || !count) return fail_msg("act_engine_get_timing: null argument");
     CK(cudaSetDevice(e->device));
     for (int k = 0; k < K_KINDS; k++) { ms[k] = 0; count[k] = 0; }
@@ -493,7 +509,8 @@ static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, 
                               u32* refunds, u32* nullifiers, u8* status) {
     CK(cudaMemsetAsync(s->flags, 0, m * 4, st));
     unsigned rgrid = m < s->range_grid ? (unsigned)m : s->range_grid;
-    LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<rgrid, ACT_L, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->flags, s->tabs)));
+    LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<rgrid, ACT_L, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->flags, s->tabs, s->cpts)));
+    LAUNCH(e, K_ENCODE, st, (spend_encode_kernel<<<nblocks(m * ACT_ENC_PARTS, ACT_ENC_BLOCK), ACT_ENC_BLOCK, 0, st>>>(e->d_ctx, m, s->cpts, s->items)));
     LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->kprime, s->flags)));
     LAUNCH(e, K_CHUNK, st, (spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, s->items, s->cvs)));
     LAUNCH(e, K_FINISH, st, (spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status)));
@@ -506,15 +523,33 @@ extern "C" int act_batch_verify_spend_and_refund_dev(act_engine* e, size_t n, co
     if (!e) return fail_msg("null engine");
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    cudaStream_t user = stream ? (cudaStream_t)stream : e->stream[0];
     size_t cap = n < ACT_SPEND_CHUNK ? n : ACT_SPEND_CHUNK;
-    int rc = ensure_scratch(&e->scratch[0], cap);
-    if (rc) return rc;
-    for (size_t off = 0; off < n; off += ACT_SPEND_CHUNK) {
+    int rc;
+    // chunks alternate over the engine's two streams (each with its own scratch) so that the thread-per-proof
+    // kernels of one chunk overlap the range kernel of the next; fork from / join into the caller's stream.
+    bool two = n > ACT_SPEND_CHUNK;
+    if ((rc = ensure_scratch(&e->scratch[0], cap))) return rc;
+    if (two && (rc = ensure_scratch(&e->scratch[1], cap))) return rc;
+    if (two) {
+        CK(cudaEventRecord(e->fork, user));
+        CK(cudaStreamWaitEvent(e->stream[0], e->fork, 0));
+        CK(cudaStreamWaitEvent(e->stream[1], e->fork, 0));
+    }
+    size_t ci = 0;
+    for (size_t off = 0; off < n; off += ACT_SPEND_CHUNK, ci++) {
         size_t m = n - off < ACT_SPEND_CHUNK ? n - off : ACT_SPEND_CHUNK;
-        rc = spend_chunk_launch(e, &e->scratch[0], st, m, (const u32*)proofs + off * ACT_PROOF_WORDS, (const u32*)rnd + off * 32,
+        int slot = two ? (int)(ci & 1) : 0;
+        cudaStream_t st = two ? e->stream[slot] : user;
+        rc = spend_chunk_launch(e, &e->scratch[slot], st, m, (const u32*)proofs + off * ACT_PROOF_WORDS, (const u32*)rnd + off * 32,
                                 (u32*)refunds + off * 32, (u32*)nullifiers + off * 8, (u8*)status + off);
         if (rc) return rc;
+    }
+    if (two) {
+        CK(cudaEventRecord(e->join[0], e->stream[0]));
+        CK(cudaEventRecord(e->join[1], e->stream[1]));
+        CK(cudaStreamWaitEvent(user, e->join[0], 0));
+        CK(cudaStreamWaitEvent(user, e->join[1], 0));
     }
     return 0;
 }

@@ -167,6 +167,36 @@ ACT_NOINLINE void ristretto_encode_(u32* w, const ge* pp) {
     fe s = fe_abs(fe_mul(den_inv, fe_sub(p.Z, Y)));
     fe_to_words(w, s);
 }
+// ---- batched double-and-encode ----------------------------------------------------------------------
+// encode(2P) without a square root (the technique of dalek's RistrettoPoint::double_and_compress_batch):
+// with e = 2XY, f = Z^2 + dT^2, g = Y^2 + X^2, h = Z^2 - dT^2 the encoding of 2P needs only 1/(e g f h), and
+// inverses batch (Montgomery's trick: one field inversion per batch + 3 multiplications per point).
+// A caller that wants encode(Q) computes P = Q/2 by halving its scalars (sc_half).
+// e*g*f*h = 0 exactly when P is 4-torsion, i.e. 2P is in the identity coset, whose encoding is 32 zero bytes.
+struct ge_dbl_enc { fe e, f, g, h, eg, fh; };
+ACT_FN ge_dbl_enc ge_dbl_enc_prepare(const ge& P) {
+    ge_dbl_enc s;
+    fe XX = fe_sq(P.X), YY = fe_sq(P.Y), ZZ = fe_sq(P.Z);
+    fe dTT = fe_mul(fe_sq(P.T), FE_D);
+    s.e = fe_mul(P.X, fe_add(P.Y, P.Y));
+    s.f = fe_add(ZZ, dTT); s.g = fe_add(YY, XX); s.h = fe_sub(ZZ, dTT);
+    s.eg = fe_mul(s.e, s.g); s.fh = fe_mul(s.f, s.h);
+    return s;
+}
+// inv = 1/(eg*fh); writes the 8 canonical words of encode(2P)
+ACT_FN void ge_dbl_enc_finish(u32* w, const ge_dbl_enc& s, const fe& inv) {
+    fe Zinv = fe_mul(s.eg, inv), Tinv = fe_mul(s.fh, inv);
+    u32 neg1 = fe_is_negative(fe_mul(s.eg, Zinv));
+    fe e = fe_select(s.e, s.g, neg1);
+    fe g = fe_select(s.g, fe_neg(s.e), neg1);
+    fe h = fe_select(s.h, fe_mul(s.f, FE_SQRT_M1), neg1);
+    fe magic = fe_select(FE_INVSQRT_A_MINUS_D, FE_SQRT_M1, neg1);
+    u32 neg2 = fe_is_negative(fe_mul(fe_mul(h, e), Zinv));
+    g = fe_cneg(g, neg2);
+    fe sres = fe_abs(fe_mul(fe_sub(h, g), fe_mul(magic, fe_mul(g, Tinv))));
+    fe_to_words(w, sres);
+}
+
 // RFC 9496 4.3.4 MAP / dalek elligator_ristretto_flavor
 ACT_NOINLINE void ristretto_elligator_(ge* out, const fe* r0p) {
     fe r0 = *r0p;

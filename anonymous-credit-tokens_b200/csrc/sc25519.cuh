@@ -111,6 +111,19 @@ ACT_NOINLINE void sc_invert_(sc* out, const sc* in) {
 }
 ACT_FN sc sc_invert(const sc& a) { sc r; sc_invert_(&r, &a); return r; }
 
+// s/2 mod l (l is odd): (s + (s odd ? l : 0)) >> 1.  Public scalars only (used to halve verification scalars so that
+// the batched double-and-encode of ge25519.cuh yields the encoding of the original point).
+ACT_FN sc sc_half(const sc& s) {
+    u32 m = 0u - (s.v[0] & 1u);
+    u32 t[9];
+    u64 c = 0;
+    ACT_UNROLL for (int i = 0; i < 8; i++) { c += (u64)s.v[i] + (SC_L_[i] & m); t[i] = (u32)c; c >>= 32; }
+    t[8] = (u32)c;
+    sc r;
+    ACT_UNROLL for (int i = 0; i < 8; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    return r;
+}
+
 // ---- signed fixed-window recoding ----------------------------------------------------------------
 // digits d_i in [-2^(W-1), 2^(W-1)) with s = sum d_i 2^(W i): d_i = window_i(s + C) - 2^(W-1), where
 // C has 2^(W-1) in every window.  One 256-bit addition instead of a carry-propagating digit loop;

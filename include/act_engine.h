@@ -115,9 +115,9 @@ ACT_API uint64_t act_engine_launch_count(const act_engine* e);
 
 /* Optional per-kernel device timing: when enabled every launch is bracketed by CUDA events on its stream.
  * act_engine_get_timing sums and clears them per kernel kind: 0 spend_range, 1 spend_head, 2 spend_chunk (hash),
- * 3 spend_finish, 4 refund_sign, 5 issue, 6 issuance_check, 7 refund_check. */
+ * 3 spend_finish, 4 refund_sign, 5 issue, 6 issuance_check, 7 refund_check, 8 spend_encode. */
 ACT_API int act_engine_set_timing(act_engine* e, int enable);
-ACT_API int act_engine_get_timing(act_engine* e, double ms[8], uint64_t count[8]);
+ACT_API int act_engine_get_timing(act_engine* e, double ms[9], uint64_t count[9]);
 /* Measured integer-multiply roofline of the device: sustained 32x32+64->64 multiply-adds per second. */
 ACT_API int act_measure_int_mul_peak(int device, double* limb_macs_per_s);
 

@@ -101,8 +101,11 @@ EXPORT void hs_refund(const hs_ctx* H, size_t n, const uint8_t* proofs, const ui
     std::vector<u32> items(n * (size_t)ACT_ITEM_WORDS + 8), cn(n * (size_t)ACT_L * 24 + 8), kp(n * 32 + 8), flags(n + 1, 0),
         cvs(n * ACT_SPEND_CHUNKS * 8 + 8), ro(n * 32 + 8), no(n * 8 + 8);
     std::vector<vb_table> tabs(ACT_RANGE_SPLIT);
+    std::vector<u32> cpts(n * 2 * ACT_L * 32 + 8);
     for (size_t p = 0; p < n; p++)
-        for (int j = 0; j < ACT_L; j++) spend_range_thread(&H->c, p, j, pf.data(), items.data(), cn.data(), flags.data(), tabs.data());
+        for (int j = 0; j < ACT_L; j++) spend_range_thread(&H->c, p, j, pf.data(), items.data(), cn.data(), flags.data(), tabs.data(), cpts.data());
+    for (size_t p = 0; p < n; p++)
+        for (int part = 0; part < 2 * ACT_L / ACT_ENC_BATCH; part++) spend_encode_thread(&H->c, p, part, cpts.data(), items.data());
     for (size_t p = 0; p < n; p++) spend_head_thread(&H->c, p, pf.data(), items.data(), cn.data(), kp.data(), flags.data());
     for (size_t p = 0; p < n; p++)
         for (int c = 0; c < ACT_SPEND_CHUNKS; c++) spend_chunk_thread(&H->c, p, c, items.data(), cvs.data());
@@ -170,3 +173,20 @@ EXPORT void hs_recode(const uint8_t s[32], int w, int8_t* digits) {
     if (w == 4) { sc b = sc_bias<4>(k); for (int i = 0; i < 64; i++) digits[i] = (int8_t)sc_digit<4>(b, i); }
     else { sc b = sc_bias<8>(k); for (int i = 0; i < 32; i++) { int d = sc_digit<8>(b, i); digits[i] = (int8_t)d; } }
 }
+
+// runs the batched double-and-encode stage on 256 points given by their encodings: out[i] = encode(2 * P_i)
+EXPORT int hs_encode_stage(const uint8_t* enc /* 256 x 32 */, uint8_t* out /* 256 x 32 */) {
+    std::vector<u32> cpts(2 * ACT_L * 32 + 8), items(ACT_ITEM_WORDS + 8);
+    for (int i = 0; i < 2 * ACT_L; i++) {
+        u32 w[8]; memcpy(w, enc + 32 * i, 32); ge P;
+        if (!ristretto_decode_(&P, w)) return 0;
+        // randomise the projective representation a little: multiply by Z = i + 2
+        fe z = fe_zero(); z.v[0] = (u32)i + 2;
+        P.X = fe_mul(P.X, z); P.Y = fe_mul(P.Y, z); P.Z = fe_mul(P.Z, z); P.T = fe_mul(P.T, z);
+        memcpy(&cpts[32 * i], P.X.v, 32); memcpy(&cpts[32 * i + 8], P.Y.v, 32); memcpy(&cpts[32 * i + 16], P.Z.v, 32); memcpy(&cpts[32 * i + 24], P.T.v, 32);
+    }
+    for (int part = 0; part < 2 * ACT_L / ACT_ENC_BATCH; part++) spend_encode_thread(nullptr, 0, part, cpts.data(), items.data());
+    memcpy(out, &items[8 * 133], 256 * 32);
+    return 1;
+}
+EXPORT void hs_sc_half(const uint8_t a[32], uint8_t out[32]) { u32 w[8]; memcpy(w, a, 32); sc r = sc_half(sc_from_words(w)); memcpy(out, r.v, 32); }

@@ -46,6 +46,8 @@ def lib():
         L.hs_sc_negsub.argtypes = [vp, vp, vp, vp]
         L.hs_blake3_small.argtypes = [vp, sz, vp]
         L.hs_recode.argtypes = [vp, i32, vp]
+        L.hs_encode_stage.argtypes = [vp, vp]; L.hs_encode_stage.restype = i32
+        L.hs_sc_half.argtypes = [vp, vp]
         _lib = L
     return _lib
 

@@ -125,3 +125,25 @@ def test_golden_corpus_small():
     assert (st == g["status_issue"]).all() and (resp == g["resp"]).all()
     ref, nul, st = hs.refund(g["proofs"], g["rnd"])
     assert (st == g["status"]).all() and (ref == g["refunds"]).all() and (nul == g["nullifiers"]).all()
+
+
+def test_batched_double_and_encode_stage_with_identity_points():
+    """Stage 1b (Montgomery-batched, square-root-free encode of 2P) vs the oracle's encode(2*P), including identity
+    points inside a batch (e*g*f*h = 0 must not poison the other 15 points of the batch)."""
+    rnd = random.Random(8)
+    encs = []
+    for i in range(256):
+        if i in (0, 5, 16, 17, 255) or (32 <= i < 48):
+            encs.append(bytes(32))                         # identity; one whole batch of identities too
+        else:
+            encs.append(O.scalarmult_base(b32(rnd.getrandbits(252))))
+    a, ap = HS._in(b"".join(encs)); o, op = HS._out(256 * 32)
+    assert HS.lib().hs_encode_stage(ap, op) == 1
+    two = b32(2)
+    for i in range(256):
+        exp = O.scalarmult(two, encs[i])
+        assert o[32 * i:32 * i + 32].tobytes() == exp, i
+    for it in range(50):
+        x = rnd.getrandbits(256)
+        h = int.from_bytes(HS.call1("hs_sc_half", b32(x)), "little")
+        assert h < ELL and (2 * h - x) % ELL == 0
