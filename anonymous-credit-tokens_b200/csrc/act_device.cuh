@@ -37,10 +37,19 @@
 #define ACT_SPEND_BYTES 15784u      // 184 + 40*390
 #define ACT_SPEND_CHUNKS 16
 
-// fixed-base tables: signed radix-256, 32 windows, entry |d| in 0..128 (0 = identity), affine Niels
-#define ACT_FB_WIN 32
-#define ACT_FB_ENT 129
+// fixed-base tables (public scalars): signed radix 2^ACT_FB_BITS, entry |d| in 0..2^(BITS-1) (0 = identity), affine
+// Niels.  BITS = 13: 20 windows x 4097 entries x 96 B = 7.9 MB per base (L2 resident), 20 mixed additions per
+// scalar multiplication instead of 32 with radix 256.
+#ifndef ACT_FB_BITS
+#define ACT_FB_BITS 13
+#endif
+#define ACT_FB_WIN ((253 + ACT_FB_BITS) / ACT_FB_BITS)
+#define ACT_FB_ENT ((1 << (ACT_FB_BITS - 1)) + 1)
 #define ACT_FB_SIZE (ACT_FB_WIN * ACT_FB_ENT)
+// table construction is split over ACT_FB_PARTS threads per window (each converts its entries to affine with
+// batched inversions of ACT_FB_BATCH points)
+#define ACT_FB_PARTS (ACT_FB_BITS > 9 ? 8 : 1)
+#define ACT_FB_BATCH 16
 // constant-time basepoint table: signed radix-16, 64 windows, |d| in 0..8
 #define ACT_CT_WIN 64
 #define ACT_CT_ENT 9
@@ -122,11 +131,22 @@ ACT_FN ge_niels load_niels(const ge_niels* p) {
 }
 
 // ---- fixed-base accumulation (public scalars) ---------------------------------------------------------
-// acc += (negate ? -s : s) * B using the radix-256 table of B: 32 mixed additions, no doublings.
+// signed radix-2^ACT_FB_BITS digit i of a scalar s < 2^253: raw window plus the carry of the window below, mapped to
+// (-2^(BITS-1), 2^(BITS-1)].  Public scalars only (the carry is data dependent).
+ACT_FN int fb_digit(const sc& s, int i, u32* carry) {
+    const u32 W = ACT_FB_BITS;
+    u32 bit = W * (u32)i, w = bit >> 5, sh = bit & 31u;
+    u32 lo = s.v[w], hi = (w + 1 < 8) ? s.v[w + 1] : 0u;
+    u32 raw = (sh ? ((lo >> sh) | (hi << (32u - sh))) : lo) & ((1u << W) - 1u);
+    int d = (int)(raw + *carry);
+    *carry = (d > (1 << (W - 1))) ? 1u : 0u;
+    return d - (int)(*carry << W);
+}
+// acc += (negate ? -s : s) * B using the wide-window table of B: ACT_FB_WIN mixed additions, no doublings.
 ACT_FN ge fb_accumulate(ge acc, const ge_niels* tab, const sc& s, bool negate) {
-    sc b = sc_bias<8>(s);
+    u32 carry = 0;
     ACT_NOUNROLL for (int i = 0; i < ACT_FB_WIN; i++) {
-        int d = sc_digit<8>(b, i);
+        int d = fb_digit(s, i, &carry);
         u32 neg = (d < 0) ? 1u : 0u;
         u32 idx = (u32)(d < 0 ? -d : d);
         if (negate) neg ^= 1u;
@@ -214,36 +234,35 @@ ACT_FN ge vb_mul_multi(const vb_table* t, const sc* s, const bool* negate) {
 }
 ACT_FN ge vb_mul(const vb_table* t, const sc& s, bool negate) { return vb_mul_multi<1>(t, &s, &negate); }
 
-// Two public scalars on ONE base with separate results (the range-proof pair com_j*gamma0_j, com_j*gamma01_j):
-// the base's doubling chain is shared.  With P_k = 2^(256k/M) P precomputed once (256(M-1)/M doublings, M tables),
+// Two public scalars on ONE base with separate results (the range-proof pair com_j*gamma0_j, com_j*gamma01_j): the
+// base's doubling chain is shared.  With P_k = 2^(256k/M) P precomputed once (256(M-1)/M doublings, M window tables),
 // each scalar costs only 256/M doublings:  s*P = sum_k 2^(256k/M) * (sum_i 16^i d_{k*WIN+i}) P.
-// Q0 = -s0*P, Q1 = -s1*P.   M = 4: 192 + 2*64 doublings instead of 2*256.
+// M = 4: 192 + 2*64 doublings instead of 2*256.  The tables are built once, then each scalar is processed on its own
+// (one accumulator live at a time: fewer registers, 4 resident blocks per SM).
 template <int M>
-ACT_FN void vb_mul_dual_split(const ge& P, const sc& s0, const sc& s1, ge* Q0, ge* Q1, vb_table* t /* M tables of scratch */) {
+ACT_FN void vb_split_tables(const ge& P, vb_table* t) {
     const int WIN = 64 / M;
-    {
-        ge Q = P;
-        ACT_NOUNROLL for (int k = 0; k < M; k++) {
-            vb_table_build(&t[k], Q);
-            if (k < M - 1) {
-                ACT_NOUNROLL for (int d = 0; d < 4 * WIN - 1; d++) Q = ge_dbl(Q, false);
-                Q = ge_dbl(Q, true);
-            }
+    ge Q = P;
+    ACT_NOUNROLL for (int k = 0; k < M; k++) {
+        vb_table_build(&t[k], Q);
+        if (k < M - 1) {
+            ACT_NOUNROLL for (int d = 0; d < 4 * WIN; d++) Q = ge_dbl_u(Q, d == 4 * WIN - 1);
         }
     }
-    sc b0 = sc_bias<4>(s0), b1 = sc_bias<4>(s1);
-    ge a0 = ge_identity(), a1 = ge_identity();
+}
+// -s * P from the tables of vb_split_tables
+template <int M>
+ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
+    const int WIN = 64 / M;
+    sc b = sc_bias<4>(s);
+    ge a = ge_identity();
     ACT_NOUNROLL for (int i = WIN - 1; i >= 0; i--) {
         if (i != WIN - 1) {
-            a0 = ge_dbl(a0, false); a0 = ge_dbl(a0, false); a0 = ge_dbl(a0, false); a0 = ge_dbl(a0, true);
-            a1 = ge_dbl(a1, false); a1 = ge_dbl(a1, false); a1 = ge_dbl(a1, false); a1 = ge_dbl(a1, true);
+            ACT_NOUNROLL for (int d = 0; d < 4; d++) a = ge_dbl_u(a, d == 3);
         }
-        ACT_NOUNROLL for (int k = 0; k < M; k++) {
-            a0 = ge_add_cached(a0, vb_lookup(&t[k], sc_digit<4>(b0, k * WIN + i), true));
-            a1 = ge_add_cached(a1, vb_lookup(&t[k], sc_digit<4>(b1, k * WIN + i), true));
-        }
+        ACT_NOUNROLL for (int k = 0; k < M; k++) a = ge_add_cached(a, vb_lookup(&t[k], sc_digit<4>(b, k * WIN + i), true));
     }
-    *Q0 = a0; *Q1 = a1;
+    return a;
 }
 // s * P for a secret s
 ACT_NOINLINE void vb_mul_ct_(ge* out, const ge* P, const sc* s) {
@@ -429,23 +448,27 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
     }
     // Every scalar is HALVED: this stage produces C'/2 and the encode stage emits encode(2 * C'/2) with one batched
     // inversion per 16 points instead of one inverse square root per point.
-    sc gamma = load_scalar(pf + 8 * 132);
-    sc g0f = load_scalar(pf + 8 * (140 + j));
-    sc g0 = sc_half(g0f);
-    sc g1 = sc_half(sc_sub(gamma, g0f));                                                    // gamma01[j] / 2  (:801,811)
-    sc z0 = sc_half(load_scalar(pf + 8 * (268 + 2 * j))), z1 = sc_half(load_scalar(pf + 8 * (269 + 2 * j)));
-    ge Q0, Q1;
-    vb_mul_dual_split<ACT_RANGE_SPLIT>(P, g0, g1, &Q0, &Q1, tabs);   // -com_j*gamma0_j/2, -com_j*gamma01_j/2
-    // C'_j0 = [h2*w00 +] h3*z_j0 - com_j*gamma0_j                                          (:806-807,814-815)
-    Q0 = fb_accumulate(Q0, C->fb[ACT_BASE_H3], z0, false);
-    if (j == 0) Q0 = fb_accumulate(Q0, C->fb[ACT_BASE_H2], sc_half(load_scalar(pf + 8 * 138)), false);
-    // C'_j1 = [h2*w01 +] h3*z_j1 - (com_j - h1)*gamma01_j = ... + h1*gamma01_j - com_j*gamma01_j   (:808-809,816)
-    Q1 = fb_accumulate(Q1, C->fb[ACT_BASE_H3], z1, false);
-    Q1 = fb_accumulate(Q1, C->fb[ACT_BASE_H1], g1, false);
-    if (j == 0) Q1 = fb_accumulate(Q1, C->fb[ACT_BASE_H2], sc_half(load_scalar(pf + 8 * 139)), false);
+    vb_split_tables<ACT_RANGE_SPLIT>(P, tabs);
     u32* cp = cpts + ((size_t)2 * ACT_L * p + 2 * j) * 32;
-    store_fe(cp, Q0.X); store_fe(cp + 8, Q0.Y); store_fe(cp + 16, Q0.Z); store_fe(cp + 24, Q0.T);
-    store_fe(cp + 32, Q1.X); store_fe(cp + 40, Q1.Y); store_fe(cp + 48, Q1.Z); store_fe(cp + 56, Q1.T);
+    ACT_NOUNROLL for (int b = 0; b < 2; b++) {
+        // b = 0: C'_j0 = [h2*w00 +] h3*z_j0 - com_j*gamma0_j                                 (:806-807,814-815)
+        // b = 1: C'_j1 = [h2*w01 +] h3*z_j1 + h1*gamma01_j - com_j*gamma01_j                 (:808-809,816)
+        //        (the reference's base com_j - H1 is never formed: -(com_j - h1)*g = h1*g - com_j*g)
+        // Scalars are re-derived from the proof bytes where they are used: nothing but the accumulator stays live.
+        sc gb = load_scalar(pf + 8 * (140 + j));
+        if (b) gb = sc_sub(load_scalar(pf + 8 * 132), gb);                                  // gamma01[j] (:801,811)
+        gb = sc_half(gb);
+        ge Q = vb_mul_split_neg<ACT_RANGE_SPLIT>(tabs, gb);
+        ACT_NOUNROLL for (int t = 0; t < 3; t++) {
+            const ge_niels* tab;
+            sc s;
+            if (t == 0) { tab = C->fb[ACT_BASE_H3]; s = load_scalar(pf + 8 * (268 + 2 * j + b)); }
+            else if (t == 1) { if (!b) continue; tab = C->fb[ACT_BASE_H1]; s = sc_sub(load_scalar(pf + 8 * 132), load_scalar(pf + 8 * (140 + j))); }
+            else { if (j != 0) continue; tab = C->fb[ACT_BASE_H2]; s = load_scalar(pf + 8 * (138 + b)); }
+            Q = fb_accumulate(Q, tab, sc_half(s), false);
+        }
+        store_fe(cp + 32 * b, Q.X); store_fe(cp + 32 * b + 8, Q.Y); store_fe(cp + 32 * b + 16, Q.Z); store_fe(cp + 32 * b + 24, Q.T);
+    }
 }
 
 // =============================================================================================================
@@ -665,6 +688,41 @@ ACT_FN void build_table_thread(const ge* B, int win, ge_niels* tab) {
     ACT_NOUNROLL for (int k = 1; k < ENT; k++) {
         row[k] = ge_to_niels(Q);
         Q = ge_add_cached(Q, Pc);
+    }
+}
+// The wide-window tables: thread (win, part) writes entries part*N+1 .. part*N+N (N = (ENT-1)/PARTS) of window `win`,
+// converting to affine with one field inversion per ACT_FB_BATCH points (Montgomery's trick).  Part 0 also writes
+// the identity entry 0.
+ACT_FN void build_fb_table_thread(const ge* B, int win, int part, ge_niels* tab) {
+    const int N = (ACT_FB_ENT - 1) / ACT_FB_PARTS;
+    ge P = *B;
+    ACT_NOUNROLL for (int i = 0; i < ACT_FB_BITS * win; i++) P = ge_dbl(P, true);
+    ge_cached Pc = ge_to_cached(P);
+    ge_niels* row = tab + (size_t)win * ACT_FB_ENT;
+    if (part == 0) row[0] = ge_niels_identity();
+    // Q = (part * N) * P : N is a power of two
+    ge Q = ge_identity();
+    if (part > 0) {
+        ge S = P;
+        ACT_NOUNROLL for (int n = N; n > 1; n >>= 1) S = ge_dbl(S, true);
+        ge_cached Sc = ge_to_cached(S);
+        ACT_NOUNROLL for (int k = 0; k < part; k++) Q = ge_add_cached(Q, Sc);
+    }
+    ACT_NOUNROLL for (int k0 = 0; k0 < N; k0 += ACT_FB_BATCH) {
+        fe xs[ACT_FB_BATCH], ys[ACT_FB_BATCH], zs[ACT_FB_BATCH], prefix[ACT_FB_BATCH];
+        fe acc = fe_one();
+        ACT_NOUNROLL for (int i = 0; i < ACT_FB_BATCH; i++) {
+            Q = ge_add_cached(Q, Pc);
+            xs[i] = Q.X; ys[i] = Q.Y; zs[i] = Q.Z;
+            prefix[i] = acc;
+            acc = fe_mul(acc, Q.Z);
+        }
+        fe inv = fe_invert(acc);
+        ACT_NOUNROLL for (int i = ACT_FB_BATCH - 1; i >= 0; i--) {
+            fe zi = fe_mul(inv, prefix[i]);
+            inv = fe_mul(inv, zs[i]);
+            row[part * N + k0 + i + 1] = ge_affine_to_niels(fe_mul(xs[i], zi), fe_mul(ys[i], zi));
+        }
     }
 }
 // Params::new (src/lib.rs:291-354).  dom: the "ACT-v1:..." separator as bytes (dlen <= 800).

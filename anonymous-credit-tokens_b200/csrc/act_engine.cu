@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issuance_check_kernel(cons
 // One block of 128 threads works on one proof at a time: thread j owns com_j and the pair C'_j0, C'_j1.  The grid is
 // sized to the machine (SMs x resident blocks) and strides over the chunk, so the per-thread window tables live in a
 // scratch buffer indexed by (block, thread) that stays small enough to sit in L2 whatever the batch size.
-#define ACT_RANGE_BLOCKS_PER_SM 3
+#ifndef ACT_RANGE_BLOCKS_PER_SM
+#define ACT_RANGE_BLOCKS_PER_SM 4   // 128 registers per thread; measured 153k vs 146k proofs/s at 3
+#endif
 __global__ void __launch_bounds__(ACT_L, ACT_RANGE_BLOCKS_PER_SM) spend_range_kernel(const act_ctx* C, size_t m, const u32* proofs, u32* items, u32* com_niels, u32* flags, vb_table* tabs, u32* cpts) {
     vb_table* mine = tabs + ((size_t)blockIdx.x * ACT_L + threadIdx.x) * ACT_RANGE_SPLIT;
     for (size_t p = blockIdx.x; p < m; p += gridDim.x) spend_range_thread(C, p, threadIdx.x, proofs, items, com_niels, flags, mine, cpts);
@@ -82,10 +84,13 @@ __global__ void setup_decode_kernel(const u32* enc /* 4 x 8 words: H1,H2,H3,W */
         *ok = v;
     }
 }
-// grid: 4 bases x 32 windows (vartime radix-256 tables), one thread each
+// the wide-window tables of G, H1, H2, H3: one thread per (base, window, part)
 __global__ void build_fb_tables_kernel(const ge* bases, ge_niels* tabs) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < 4 * ACT_FB_WIN) build_table_thread<8, ACT_FB_ENT>(&bases[t / ACT_FB_WIN], t % ACT_FB_WIN, tabs + (size_t)(t / ACT_FB_WIN) * ACT_FB_SIZE);
+    if (t < 4 * ACT_FB_WIN * ACT_FB_PARTS) {
+        int part = t % ACT_FB_PARTS, win = (t / ACT_FB_PARTS) % ACT_FB_WIN, base = t / (ACT_FB_PARTS * ACT_FB_WIN);
+        build_fb_table_thread(&bases[base], win, part, tabs + (size_t)base * ACT_FB_SIZE);
+    }
 }
 __global__ void build_ct_table_kernel(const ge* bases, ge_niels* tab) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,7 +340,7 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         CKB(cudaMemcpy(d_enc, h, 96, cudaMemcpyHostToDevice));
         CKB(cudaMemcpy(d_enc + 24, pk_w, 32, cudaMemcpyHostToDevice));
         setup_decode_kernel<<<1, 1>>>(d_enc, e->d_bases, d_W, d_ok);
-        build_fb_tables_kernel<<<4, ACT_FB_WIN>>>(e->d_bases, e->d_tables);
+        build_fb_tables_kernel<<<(4 * ACT_FB_WIN * ACT_FB_PARTS + 31) / 32, 32>>>(e->d_bases, e->d_tables);
         build_ct_table_kernel<<<1, ACT_CT_WIN>>>(e->d_bases, e->d_tables + 4 * (size_t)ACT_FB_SIZE);
         CKB(cudaGetLastError());
         u32 ok = 0;
@@ -417,23 +422,38 @@ extern "C" int act_engine_get_timing(act_engine* e, double ms[9], uint64_t count
     return 0;
 }
 
-// Integer-multiply roofline of this GPU: sustained rate of independent 32x32+64->64 multiply-adds
-// (IMAD.WIDE.U32), in limb-MACs per second.
+// Integer-multiply roofline of this GPU: sustained rate of 32x32+64->64 multiply-adds (IMAD.WIDE.U32) with
+// operands that change every iteration (a loop-invariant product would be hoisted and the loop would time 64-bit
+// additions instead), in limb-MACs per second.  Eight independent accumulators per thread, 64 warps per SM.
 #define PEAK_ITER 4096
 __global__ void __launch_bounds__(256) int_mul_peak_kernel(u32* out, u32 a0, u32 b0) {
-    u32 a = a0 + threadIdx.x, b = b0 + blockIdx.x;
-    u64 acc[8];
+    u32 a[8], b = (b0 + blockIdx.x) | 1u;
+    u32 c[16];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = i;
+    for (int i = 0; i < 8; i++) { c[2 * i] = i; c[2 * i + 1] = 0; a[i] = a0 * (threadIdx.x + 1) + i; }
 #pragma unroll 1
     for (int it = 0; it < PEAK_ITER; it++) {
+        // the mad.lo.cc / madc.hi pair is what the field multiplication uses; ptxas fuses it into one IMAD.WIDE.U32
+        // with a 64-bit addend (a plain mad.wide.u32 with a 64-bit accumulator gets split into a multiply and an add)
+        asm volatile(
+            "mad.lo.cc.u32 %0, %16, %24, %0;\n\tmadc.hi.u32 %1, %16, %24, %1;\n\t"
+            "mad.lo.cc.u32 %2, %17, %24, %2;\n\tmadc.hi.u32 %3, %17, %24, %3;\n\t"
+            "mad.lo.cc.u32 %4, %18, %24, %4;\n\tmadc.hi.u32 %5, %18, %24, %5;\n\t"
+            "mad.lo.cc.u32 %6, %19, %24, %6;\n\tmadc.hi.u32 %7, %19, %24, %7;\n\t"
+            "mad.lo.cc.u32 %8, %20, %24, %8;\n\tmadc.hi.u32 %9, %20, %24, %9;\n\t"
+            "mad.lo.cc.u32 %10, %21, %24, %10;\n\tmadc.hi.u32 %11, %21, %24, %11;\n\t"
+            "mad.lo.cc.u32 %12, %22, %24, %12;\n\tmadc.hi.u32 %13, %22, %24, %13;\n\t"
+            "mad.lo.cc.u32 %14, %23, %24, %14;\n\tmadc.hi.u32 %15, %23, %24, %15;"
+            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(c[8]), "+r"(c[9]),
+              "+r"(c[10]), "+r"(c[11]), "+r"(c[12]), "+r"(c[13]), "+r"(c[14]), "+r"(c[15])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b));
 #pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+        for (int i = 0; i < 8; i++) a[i] ^= c[2 * i];   // one ALU-pipe instruction per multiply-add keeps the product loop-variant
     }
-    u64 s = 0;
+    u32 s = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) s += acc[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = (u32)s ^ (u32)(s >> 32);
+    for (int i = 0; i < 16; i++) s ^= c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 extern "C" int act_measure_int_mul_peak(int device, double* limb_macs_per_s) {
     if (!limb_macs_per_s) return fail_msg("null argument");

@@ -33,11 +33,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "spend_verify_refund_per_sec"
 UNIT = "proofs/s"
-# algorithmic work per unit: 32x32->64 limb multiply-accumulates
-LIMB_MACS_PER_SPEND = 4.8e7
-LIMB_MACS_PER_SPEND_RANGE = 4.32e7   # stage-1 kernel: 128 decodes + the 256 range-proof commitments (their 256 encodings,
-                                     # 3.4e6, are the separate encode stage; head + sign are 1.4e6)
-LIMB_MACS_PER_ISSUE = 7.0e5
+# Algorithmic work per unit in 32x32+64->64 limb multiply-accumulates (field multiply M = 72, square S = 44), counted for
+# the algorithm this engine implements (DESIGN.md section 4 has the breakdown; SURVEY.md 8d estimated 4.8e7 / 7.0e5 for
+# a wNAF formulation -- the implemented shared-chain / wide-window / batched-encode algorithm needs less):
+#   range kernel per com_j: 1506 S + 2699 M = 2.606e5  -> x128 = 3.34e7 per proof
+#   encode 7.1e5, head 9.9e5, sign 4.6e5 per proof
+LIMB_MACS_PER_SPEND_RANGE = 3.34e7
+LIMB_MACS_PER_SPEND = 3.34e7 + 7.1e5 + 9.9e5 + 4.6e5
+LIMB_MACS_PER_ISSUE = 6.7e5
+# IMAD.WIDE.U32 issues at 32 lanes per clock per SM on sm_100 (ncu: 2 fma-heavy pipe cycles per warp instruction at
+# 0.5 instructions/clock/SMSP; profiles/r01d_*.txt) -> integer-multiply roofline = SMs x 32 x SM clock
+IMAD_WIDE_LANES_PER_CLK_PER_SM = 32
 PROOF_BYTES = 16832
 UNIQUE_PROOFS = 2048                 # unique valid proofs synthesised on the CPU, tiled to the batch size
 UNIQUE_REQUESTS = 16384
@@ -190,7 +196,8 @@ def main():
     params = act.Params.new(*corpus.BENCH_PARAMS, device=local)
     assert params.h == ctx.h, "Params::new differs from the oracle"
     eng = act.Engine(params, act.PrivateKey(ctx.x, ctx.w), device=local)
-    peak = act.measure_int_mul_peak(local)
+    peak_microbench = act.measure_int_mul_peak(local)
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
 
     def tile_to(dst_t, src_np, rec, count, shift):
         """fill device tensor with `count` records by tiling the unique set (rotated by `shift` records)."""
@@ -255,6 +262,8 @@ def main():
     launches = eng.launch_count - launches0
     clocks = clk.summary()
     value = world * n * K / (ms * 1e-3)
+    sm_hz = 1e6 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    peak = sm_count * IMAD_WIDE_LANES_PER_CLK_PER_SM * sm_hz
     # ---- roofline pass: the same work in slices of one pipeline chunk on ONE stream (no inter-chunk overlap), every launch
     # bracketed by CUDA events on that stream, so that per-kernel durations are clean ----
     SL = 16384
@@ -287,11 +296,22 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture (bytes per proof x proofs per launch)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = {"bytes_per_launch": tj["spend_range_dram_bytes_per_proof"] * per_launch_proofs, "bytes_per_proof": tj["spend_range_dram_bytes_per_proof"],
+                   "algorithmic_bytes_per_proof": PROOF_BYTES + 128 * 96 + 256 * 128 + 128 * 32, "source": tj.get("source")}
+    except Exception:
+        pass
     roofline = {
         "bound": "int_mul", "kernel": "spend_range_kernel", "achieved": achieved / 1e12 if achieved else None, "peak": peak / 1e12,
-        "unit": "Tlimb-MAC/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-        "peak_source": "measured live: act_measure_int_mul_peak (independent IMAD.WIDE.U32 chains, 32x32+64->64)",
-        "work_per_unit": f"{LIMB_MACS_PER_SPEND_RANGE:.3g} limb-MACs per proof in this kernel (SURVEY 8d: 4.8e7 per spend, minus 256 encodings 3.4e6 and head/sign 1.4e6)",
+        "unit": "Tlimb-MAC/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+        "peak_source": f"{sm_count} SMs x {IMAD_WIDE_LANES_PER_CLK_PER_SM} IMAD.WIDE lanes/clk x {sm_hz / 1e6:.0f} MHz (SM clock sampled under load); "
+                       "pipe rate from ncu (sm__pipe_fmaheavy_cycles_active: 2 cycles per IMAD.WIDE warp instruction); there is no integer entry in MEASURED_PEAKS.json",
+        "peak_microbench": peak_microbench / 1e12,
+        "peak_microbench_note": "act_measure_int_mul_peak: live IMAD.WIDE chain loop (includes ptxas register-pair moves on the same pipe, so it is a lower bound)",
+        "work_per_unit": f"{LIMB_MACS_PER_SPEND_RANGE:.3g} limb-MACs per proof in this kernel = 128 x (1506 S x 44 + 2699 M x 72), the implemented algorithm (DESIGN.md 4)",
         "timing": "separate pass, one stream, slices of 16384 proofs, CUDA events around every launch",
         "kernel_share_of_step": rng_ms / total_kernel_ms if total_kernel_ms else None,
         "kernel_ms": {k: round(v[0], 3) for k, v in ktimes.items() if v[1]},

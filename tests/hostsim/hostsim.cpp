@@ -47,7 +47,8 @@ EXPORT hs_ctx* hs_ctx_create(const uint8_t h[96], const uint8_t x[32], const uin
     if (!ok) { delete H; return nullptr; }
     H->tables.resize(4 * (size_t)ACT_FB_SIZE + ACT_CT_SIZE);
     for (int b = 0; b < 4; b++)
-        for (int win = 0; win < ACT_FB_WIN; win++) build_table_thread<8, ACT_FB_ENT>(&bases[b], win, H->tables.data() + (size_t)b * ACT_FB_SIZE);
+        for (int win = 0; win < ACT_FB_WIN; win++)
+            for (int part = 0; part < ACT_FB_PARTS; part++) build_fb_table_thread(&bases[b], win, part, H->tables.data() + (size_t)b * ACT_FB_SIZE);
     for (int win = 0; win < ACT_CT_WIN; win++) build_table_thread<4, ACT_CT_ENT>(&bases[0], win, H->tables.data() + 4 * (size_t)ACT_FB_SIZE);
     for (int b = 0; b < 4; b++) H->c.fb[b] = H->tables.data() + (size_t)b * ACT_FB_SIZE;
     H->c.ct_g = H->tables.data() + 4 * (size_t)ACT_FB_SIZE;
