@@ -130,6 +130,19 @@ ACT_FN ge_niels load_niels(const ge_niels* p) {
     return r;
 }
 
+// L1 prefetch of a table line that a later step of the same thread will read (no register is tied up while the
+// line travels from L2 / HBM)
+#ifndef ACT_PREFETCH
+#define ACT_PREFETCH 1
+#endif
+ACT_FN void prefetch_line(const void* p) {
+#if ACT_PTX && ACT_PREFETCH
+    asm volatile("prefetch.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // ---- fixed-base accumulation (public scalars) ---------------------------------------------------------
 // signed radix-2^ACT_FB_BITS digit i of a scalar s < 2^253: raw window plus the carry of the window below, mapped to
 // (-2^(BITS-1), 2^(BITS-1)].  Public scalars only (the carry is data dependent).
@@ -145,12 +158,18 @@ ACT_FN int fb_digit(const sc& s, int i, u32* carry) {
 // acc += (negate ? -s : s) * B using the wide-window table of B: ACT_FB_WIN mixed additions, no doublings.
 ACT_FN ge fb_accumulate(ge acc, const ge_niels* tab, const sc& s, bool negate) {
     u32 carry = 0;
+    int d = fb_digit(s, 0, &carry);
     ACT_NOUNROLL for (int i = 0; i < ACT_FB_WIN; i++) {
-        int d = fb_digit(s, i, &carry);
         u32 neg = (d < 0) ? 1u : 0u;
         u32 idx = (u32)(d < 0 ? -d : d);
         if (negate) neg ^= 1u;
-        ge_niels e = load_niels(tab + i * ACT_FB_ENT + idx);
+        const ge_niels* cur = tab + i * ACT_FB_ENT + idx;
+        if (i + 1 < ACT_FB_WIN) {   // next window's entry (96 B: may straddle two lines) travels while this addition runs
+            d = fb_digit(s, i + 1, &carry);
+            const ge_niels* nxt = tab + (i + 1) * ACT_FB_ENT + (u32)(d < 0 ? -d : d);
+            prefetch_line(nxt); prefetch_line(reinterpret_cast<const u8*>(nxt) + 95);
+        }
+        ge_niels e = load_niels(cur);
         acc = ge_add_niels(acc, ge_niels_cneg(e, neg));
     }
     return acc;
@@ -260,7 +279,13 @@ ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
         if (i != WIN - 1) {
             ACT_NOUNROLL for (int d = 0; d < 4; d++) a = ge_dbl_u(a, d == 3);
         }
-        ACT_NOUNROLL for (int k = 0; k < M; k++) a = ge_add_cached(a, vb_lookup(&t[k], sc_digit<4>(b, k * WIN + i), true));
+        ACT_NOUNROLL for (int k = 0; k < M; k++) {
+            if (k + 1 < M) {   // the next table's entry travels to L1 while this addition runs
+                int dn = sc_digit<4>(b, (k + 1) * WIN + i);
+                prefetch_line(&t[k + 1].e[dn < 0 ? -dn : dn]);
+            }
+            a = ge_add_cached(a, vb_lookup(&t[k], sc_digit<4>(b, k * WIN + i), true));
+        }
     }
     return a;
 }

@@ -34,6 +34,10 @@
 #define ACT_NOUNROLL
 #endif
 
+#ifndef ACT_REDUCE_ALT
+#define ACT_REDUCE_ALT 1
+#endif
+
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef uint8_t u8;
@@ -207,6 +211,23 @@ ACT_FN fe fe_reduce512(const u32* r) {
     t[8] = 0;
     // even hi limbs into slots (0,1)(2,3)(4,5)(6,7); odd hi limbs into (1,2)(3,4)(5,6)(7,8)
     fe_row_chain(t, r[8], r[10], r[12], r[14], k38);
+#if ACT_REDUCE_ALT
+    // the odd products as free-standing 64-bit values added with one carry chain on the ALU pipe: the slots (1,2)(3,4)..
+    // are not even-aligned register pairs, and as multiply-add addends they cost one IMAD.MOV each on the multiply pipe
+    {
+        u64 q0 = (u64)r[9] * 38u, q1 = (u64)r[11] * 38u, q2 = (u64)r[13] * 38u, q3 = (u64)r[15] * 38u;
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+            : "r"((u32)q0), "r"((u32)(q0 >> 32)), "r"((u32)q1), "r"((u32)(q1 >> 32)), "r"((u32)q2), "r"((u32)(q2 >> 32)), "r"((u32)q3), "r"((u32)(q3 >> 32)));
+    }
+#else
     asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
         "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
         "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
@@ -217,6 +238,7 @@ ACT_FN fe fe_reduce512(const u32* r) {
         "madc.hi.u32 %7, %11, %12, %7;"
         : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
         : "r"(r[9]), "r"(r[11]), "r"(r[13]), "r"(r[15]), "r"(k38));
+#endif
 #else
     u64 c = 0;
     for (int i = 0; i < 8; i++) { c += (u64)r[i] + (u64)r[8 + i] * 38u; t[i] = (u32)c; c >>= 32; }

@@ -102,3 +102,115 @@ def test_empty_and_single(engine, octx, base):
     ref, nul, st = engine.batch_verify_spend_and_refund(base["proofs"][:corpus.PROOF_BYTES], base["rnd"][:128])
     o = octx.refund(base["proofs"][:corpus.PROOF_BYTES].tobytes(), base["rnd"][:128].tobytes())
     assert st[0] == o[0] == 0 and ref.tobytes() == o[1] and nul.tobytes() == o[2]
+
+
+def test_golden_trip_and_corpus_on_gpu(act):
+    """BASELINE config #1 (examples/act.rs trip) and the committed golden corpus through the C ABI:
+    no oracle call here -- the expected bytes are the committed fixtures."""
+    import json, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = json.load(open(os.path.join(here, "golden", "trip.json")))
+    import blake3
+    stream = blake3.blake3(b"act-oracle-0").digest(length=34112)
+    params = act.Params.new(*g["params"])
+    assert params.h.hex() == g["h"]
+    key = act.PrivateKey.from_secret(bytes.fromhex(g["x"]))
+    assert key.w.hex() == g["w"]
+    with act.Engine(params, key) as eng:
+        c40 = (40).to_bytes(32, "little")
+        resp, st = eng.batch_issue(bytes.fromhex(g["request"]), c40, stream[320:448])
+        assert st[0] == 0 and resp.tobytes().hex() == g["response"]
+        assert eng.batch_issuance_check(bytes.fromhex(g["request"])[:32], resp)[0] == 0
+        proof = bytes.fromhex(g["proof"])
+        ref, nul, st = eng.batch_verify_spend_and_refund(proof, stream[448 + 524 * 64:448 + 524 * 64 + 128])
+        assert st[0] == 0 and ref.tobytes().hex() == g["refund"] and nul.tobytes().hex() == g["nullifier"]
+        assert eng.batch_refund_check(proof[128:128 + 4096], ref)[0] == 0
+        assert act.encode_refund_cbor(ref).hex() == g["cbor_refund"]
+        assert act.encode_issuance_response_cbor(resp).hex() == g["cbor_response"]
+    c = np.load(os.path.join(here, "golden", "corpus_small.npz"))
+    with act.Engine(act.Params(c["h"].tobytes()), act.PrivateKey(c["x"].tobytes(), c["w"].tobytes())) as eng:
+        resp, st = eng.batch_issue(c["req"], c["cs"], c["rnd_issue"])
+        assert (st == c["status_issue"]).all() and (resp == c["resp"]).all()
+        ref, nul, st = eng.batch_verify_spend_and_refund(c["proofs"], c["rnd"])
+        assert (st == c["status"]).all() and (ref == c["refunds"]).all() and (nul == c["nullifiers"]).all()
+
+
+def test_large_mixed_adversarial_batch(engine, octx, base):
+    """BASELINE config #5 shape at a size the GPU finishes in a second: 40 000 proofs, three quarters of them tampered
+    (every mutation class of SURVEY section 4), crossing the 16 384-proof pipeline chunks and both streams with a ragged
+    tail.  Size-independent property: a tiled batch must give the tiled per-proof answers of the oracle, bit for bit;
+    then the batch replay screen (the caller's nullifier check) flags every repeated accepted nullifier."""
+    import importlib
+    import torch
+    proofs, rnd, expect, labels = corpus.mutate_proofs(octx, base)
+    u = len(expect)
+    o_ref, o_nul, o_st, _ = octx.batch_refund(proofs, rnd, threads=8)
+    n = 40000
+    idx = (np.arange(n) * 7 + 3) % u                      # a permuted tiling, so neighbours differ
+    P = proofs.reshape(u, -1)[idx].reshape(-1).copy(); R = rnd.reshape(u, -1)[idx].reshape(-1).copy()
+    ref, nul, st = engine.batch_verify_spend_and_refund(P, R)
+    assert (st == o_st[idx]).all()
+    assert (ref.reshape(n, -1) == o_ref.reshape(u, -1)[idx]).all() and (nul.reshape(n, -1) == o_nul.reshape(u, -1)[idx]).all()
+    assert 0.3 < (st != 0).mean() < 0.9 and set(np.unique(st)) >= {0, 6, 7, 0x81}
+    # rejected proofs leave zero-filled outputs
+    assert not ref.reshape(n, -1)[st != 0].any() and not nul.reshape(n, -1)[st != 0].any()
+    sh = importlib.import_module("anonymous-credit-tokens_b200.sharding")
+    flagged = sh.flag_replays(torch.from_numpy(st).cuda(), torch.from_numpy(nul).cuda()).cpu().numpy()
+    seen = set(); exp = st.copy()
+    for i in range(n):
+        if st[i] == 0:
+            k = nul[32 * i:32 * i + 32].tobytes()
+            if k in seen:
+                exp[i] = 3
+            seen.add(k)
+    assert (flagged == exp).all() and (flagged == 3).sum() > n // 8
+
+
+def test_issue_large_batch_and_device_buffers(engine, octx, base):
+    """batch_issue over 300 000 tiled requests (crosses the 262 144-request chunk) and the device-buffer entry points on
+    a non-default stream: same bytes as the host-buffer calls and as the oracle."""
+    import torch
+    req, cs, rnd, expect, labels = corpus.mutate_requests(octx, base)
+    u = len(expect)
+    o_resp, o_st, _ = octx.batch_issue(req, cs, rnd, threads=8)
+    n = 300000
+    idx = (np.arange(n) * 5 + 1) % u
+    Rq = req.reshape(u, -1)[idx].reshape(-1).copy(); Cs = cs.reshape(u, -1)[idx].reshape(-1).copy(); Rn = rnd.reshape(u, -1)[idx].reshape(-1).copy()
+    resp, st = engine.batch_issue(Rq, Cs, Rn)
+    assert (st == o_st[idx]).all() and (resp.reshape(n, -1) == o_resp.reshape(u, -1)[idx]).all()
+    # device buffers, caller's stream
+    s = torch.cuda.Stream()
+    m = 5000
+    with torch.cuda.stream(s):
+        d = [torch.from_numpy(a[:m * k]).cuda() for a, k in ((Rq, 128), (Cs, 32), (Rn, 128))]
+        d_resp = torch.zeros(m * 160, dtype=torch.uint8, device="cuda"); d_st = torch.full((m,), 99, dtype=torch.uint8, device="cuda")
+        engine.batch_issue_dev(m, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d_resp.data_ptr(), d_st.data_ptr(), s.cuda_stream)
+        proofs, prnd, _, _ = corpus.mutate_proofs(octx, base)
+        k = len(proofs) // corpus.PROOF_BYTES
+        d_p = torch.from_numpy(proofs).cuda(); d_r = torch.from_numpy(prnd).cuda()
+        d_ref = torch.zeros(k * 128, dtype=torch.uint8, device="cuda"); d_nul = torch.zeros(k * 32, dtype=torch.uint8, device="cuda")
+        d_pst = torch.full((k,), 99, dtype=torch.uint8, device="cuda")
+        engine.batch_verify_spend_and_refund_dev(k, d_p.data_ptr(), d_r.data_ptr(), d_ref.data_ptr(), d_nul.data_ptr(), d_pst.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    assert (d_st.cpu().numpy() == st[:m]).all() and (d_resp.cpu().numpy() == resp[:m * 160]).all()
+    h_ref, h_nul, h_st = engine.batch_verify_spend_and_refund(proofs, prnd)
+    assert (d_pst.cpu().numpy() == h_st).all() and (d_ref.cpu().numpy() == h_ref).all() and (d_nul.cpu().numpy() == h_nul).all()
+
+
+def test_two_gpu_sharding_matches_one_gpu(act, octx, base):
+    """Shards on two devices (when the box has them) concatenate to the single-device answer."""
+    if act.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import importlib
+    sh = importlib.import_module("anonymous-credit-tokens_b200.sharding")
+    proofs, rnd, _, _ = corpus.mutate_proofs(octx, base)
+    n = len(proofs) // corpus.PROOF_BYTES
+    params, key = act.Params(octx.h), act.PrivateKey(octx.x, octx.w)
+    with act.Engine(params, key, device=0) as e0, act.Engine(params, key, device=1) as e1:
+        full = e0.batch_verify_spend_and_refund(proofs, rnd)
+        parts = []
+        for r, e in enumerate((e0, e1)):
+            lo, hi = sh.shard_bounds(n, r, 2)
+            parts.append(e.batch_verify_spend_and_refund(proofs[lo * corpus.PROOF_BYTES:hi * corpus.PROOF_BYTES], rnd[lo * 128:hi * 128]))
+        for k in range(3):
+            assert (np.concatenate([p[k] for p in parts]) == full[k]).all()
