@@ -301,7 +301,7 @@ def main():
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = {"bytes_per_launch": tj["spend_range_dram_bytes_per_proof"] * per_launch_proofs, "bytes_per_proof": tj["spend_range_dram_bytes_per_proof"],
-                   "algorithmic_bytes_per_proof": PROOF_BYTES + 128 * 96 + 256 * 128 + 128 * 32, "source": tj.get("source")}
+                   "algorithmic_bytes_per_proof": PROOF_BYTES + 128 * 96 + 256 * 128 + 128 * 32, "source": tj.get("source"), "note": tj.get("note")}
     except Exception:
         pass
     roofline = {
