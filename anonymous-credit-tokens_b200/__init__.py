@@ -27,6 +27,10 @@ REFUND_BYTES = 128
 RND_BYTES = 128
 COM_BYTES = 4096
 L = 128
+KIND_REQUEST, KIND_RESPONSE, KIND_PROOF, KIND_REFUND = 0, 1, 2, 3
+CBOR_BYTES = {0: 141, 1: 176, 2: 18036, 3: 141}
+RECORD_BYTES = {0: 128, 1: 160, 2: 16832, 3: 128}
+NOT_CANONICAL = 0xFF
 
 # status codes (include/act_engine.h; 1 + discriminant of the reference's `Error`, src/lib.rs:102-112)
 OK = 0
@@ -61,6 +65,7 @@ EXPORTED_SYMBOLS = [
     "act_pack_issuance_requests_cbor", "act_pack_spend_proofs_cbor", "act_pack_issuance_responses_cbor",
     "act_pack_refunds_cbor", "act_encode_issuance_request_cbor", "act_encode_issuance_response_cbor",
     "act_encode_spend_proof_cbor", "act_encode_refund_cbor",
+    "act_flag_replays", "act_flag_replays_dev", "act_unpack_cbor", "act_unpack_cbor_dev", "act_encode_cbor", "act_encode_cbor_dev",
 ]
 
 
@@ -107,6 +112,12 @@ def load_library():
         f = getattr(lib, name); f.argtypes = [sz, vp, vp, vp, vp]; f.restype = i32
     for name in ("act_encode_issuance_request_cbor", "act_encode_issuance_response_cbor", "act_encode_spend_proof_cbor", "act_encode_refund_cbor"):
         f = getattr(lib, name); f.argtypes = [vp, vp]; f.restype = sz
+    lib.act_flag_replays_dev.argtypes = [vp, sz, vp, vp, sz, vp, vp, vp]; lib.act_flag_replays_dev.restype = i32
+    lib.act_flag_replays.argtypes = [vp, sz, vp, vp, sz, vp, vp]; lib.act_flag_replays.restype = i32
+    lib.act_unpack_cbor_dev.argtypes = [vp, i32, sz, vp, vp, vp, vp]; lib.act_unpack_cbor_dev.restype = i32
+    lib.act_encode_cbor_dev.argtypes = [vp, i32, sz, vp, vp, vp]; lib.act_encode_cbor_dev.restype = i32
+    lib.act_unpack_cbor.argtypes = [vp, i32, sz, vp, vp, vp]; lib.act_unpack_cbor.restype = i32
+    lib.act_encode_cbor.argtypes = [vp, i32, sz, vp, vp]; lib.act_encode_cbor.restype = i32
     _lib = lib
     return lib
 
@@ -259,6 +270,40 @@ class Engine:
         st = np.zeros(n, np.uint8)
         _check(self.lib.act_batch_refund_check(self._h, n, cm.ctypes.data, rf.ctypes.data, st.ctypes.data), "act_batch_refund_check")
         return st
+
+    # ---- rows either side of the hot path ----
+    def flag_replays(self, status, nullifiers, seen=None):
+        """Batch replay screen (the caller's NullifierDb, src/tests.rs:28-50, in slice order): accepted proofs whose
+        nullifier occurred earlier in the batch or in `seen` (k*32 bytes) get status 3 (DoubleSpendError)."""
+        st = _u8(status); n = st.size
+        nul = _u8(nullifiers, n * 32, "nullifiers")
+        sn = _u8(seen) if seen is not None and len(seen) else np.zeros(0, np.uint8)
+        out = np.zeros(n, np.uint8)
+        _check(self.lib.act_flag_replays(self._h, n, st.ctypes.data, nul.ctypes.data, sn.size // 32, sn.ctypes.data if sn.size else None, out.ctypes.data),
+               "act_flag_replays")
+        return out
+
+    def flag_replays_dev(self, n, status, nullifiers, n_seen, seen, status_out, stream=0):
+        _check(self.lib.act_flag_replays_dev(self._h, n, status, nullifiers, n_seen, seen, status_out, stream), "act_flag_replays_dev")
+
+    def unpack_cbor(self, kind, cbor):
+        """Canonical-CBOR fast path: fixed-size items -> (records, status); status 0xFF = not the canonical skeleton."""
+        c = _u8(cbor); n = c.size // CBOR_BYTES[kind]
+        rec = np.zeros(n * RECORD_BYTES[kind], np.uint8); st = np.zeros(n, np.uint8)
+        _check(self.lib.act_unpack_cbor(self._h, kind, n, c.ctypes.data, rec.ctypes.data, st.ctypes.data), "act_unpack_cbor")
+        return rec, st
+
+    def encode_cbor(self, kind, records):
+        r = _u8(records); n = r.size // RECORD_BYTES[kind]
+        out = np.zeros(n * CBOR_BYTES[kind], np.uint8)
+        _check(self.lib.act_encode_cbor(self._h, kind, n, r.ctypes.data, out.ctypes.data), "act_encode_cbor")
+        return out
+
+    def unpack_cbor_dev(self, kind, n, cbor, records, status, stream=0):
+        _check(self.lib.act_unpack_cbor_dev(self._h, kind, n, cbor, records, status, stream), "act_unpack_cbor_dev")
+
+    def encode_cbor_dev(self, kind, n, records, cbor, stream=0):
+        _check(self.lib.act_encode_cbor_dev(self._h, kind, n, records, cbor, stream), "act_encode_cbor_dev")
 
     # ---- raw pointers (pinned host memory or torch tensors); nothing is allocated here ----
     def batch_issue_ptr(self, n, req, cs, rnd, resp, status):

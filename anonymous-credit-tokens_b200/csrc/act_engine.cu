@@ -15,6 +15,7 @@
 
 #include "../../include/act_engine.h"
 #include "act_device.cuh"
+#include "act_aux.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // kernels: thin index wrappers around the per-thread bodies in act_device.cuh
@@ -200,6 +201,8 @@ struct act_engine {
     spend_scratch scratch[2];
     io_slot io[2];
     uint64_t launches = 0;
+    int32_t* d_skel[4] = {nullptr, nullptr, nullptr, nullptr};   // canonical CBOR skeletons (request, response, proof, refund)
+    u32* d_rp_table = nullptr; size_t rp_cap = 0;                 // replay-screen hash table
     // optional per-kernel device timing (CUDA events on the launching stream)
     bool timing = false;
     struct timed { int kind; cudaEvent_t a, b; };
@@ -299,6 +302,8 @@ extern "C" void act_engine_destroy(act_engine* e) {
     cudaDeviceSynchronize();
     if (e->d_ctx) { cudaMemset(e->d_ctx, 0, sizeof(act_ctx)); cudaFree(e->d_ctx); }  // zeroise x on the device
     cudaFree(e->d_tables); cudaFree(e->d_bases);
+    for (int k = 0; k < 4; k++) cudaFree(e->d_skel[k]);
+    cudaFree(e->d_rp_table);
     if (e->fork) cudaEventDestroy(e->fork);
     for (int s = 0; s < 2; s++) if (e->join[s]) cudaEventDestroy(e->join[s]);
     for (int s = 0; s < 2; s++) {
@@ -647,4 +652,131 @@ extern "C" int act_batch_verify_spend_and_refund(act_engine* e, size_t n, const 
         if (rc) return rc;
         return spend_chunk_launch(e, &e->scratch[s], st, m, (const u32*)io.in0, (const u32*)io.in1, (u32*)io.out0, (u32*)io.out1, io.st);
     });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rows either side of the hot path (act_aux.cuh): replay screen and the canonical-CBOR fast path
+// ---------------------------------------------------------------------------------------------------
+extern "C" int act_flag_replays_dev(act_engine* e, size_t n, const void* status, const void* nullifiers, size_t n_seen, const void* seen,
+                                    void* status_out, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!status || !nullifiers || !status_out || (n_seen && !seen)) return fail_msg("act_flag_replays_dev: null buffer");
+    if (n + n_seen >= 0x7fffffffu) return fail_msg("act_flag_replays_dev: batch too large");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    size_t slots = 1024;
+    while (slots < 2 * (n + n_seen)) slots <<= 1;
+    if (e->rp_cap < slots) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(e->d_rp_table); e->d_rp_table = nullptr; e->rp_cap = 0;
+        CK(cudaMalloc((void**)&e->d_rp_table, slots * 4));
+        e->rp_cap = slots;
+    }
+    CK(cudaMemsetAsync(e->d_rp_table, 0xff, slots * 4, st));
+    u32 seed = 0x243f6a88u ^ (u32)(e->launches * 0x9e3779b9u);
+    u32 total = (u32)(n + n_seen);
+    replay_insert_kernel<<<nblocks(total, 256), 256, 0, st>>>((u32)n, (u32)n_seen, (const u8*)status, (const uint4*)seen, (const uint4*)nullifiers,
+                                                             e->d_rp_table, (u32)(slots - 1), seed);
+    replay_resolve_kernel<<<nblocks(n, 256), 256, 0, st>>>((u32)n, (u32)n_seen, (const u8*)status, (const uint4*)seen, (const uint4*)nullifiers,
+                                                           e->d_rp_table, (u32)(slots - 1), seed, (u8*)status_out);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int act_flag_replays(act_engine* e, size_t n, const uint8_t* status, const uint8_t* nullifiers, size_t n_seen, const uint8_t* seen,
+                                uint8_t* status_out) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!status || !nullifiers || !status_out || (n_seen && !seen)) return fail_msg("act_flag_replays: null buffer");
+    CK(cudaSetDevice(e->device));
+    u8 *d_st = nullptr, *d_nul = nullptr, *d_seen = nullptr, *d_out = nullptr;
+    int rc = 0;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaMalloc((void**)&d_st, n)); CKB(cudaMalloc((void**)&d_nul, n * 32)); CKB(cudaMalloc((void**)&d_out, n));
+        if (n_seen) { CKB(cudaMalloc((void**)&d_seen, n_seen * 32)); CKB(cudaMemcpyAsync(d_seen, seen, n_seen * 32, cudaMemcpyHostToDevice, e->stream[0])); }
+        CKB(cudaMemcpyAsync(d_st, status, n, cudaMemcpyHostToDevice, e->stream[0]));
+        CKB(cudaMemcpyAsync(d_nul, nullifiers, n * 32, cudaMemcpyHostToDevice, e->stream[0]));
+        if ((rc = act_flag_replays_dev(e, n, d_st, d_nul, n_seen, d_seen, d_out, e->stream[0]))) break;
+        CKB(cudaMemcpyAsync(status_out, d_out, n, cudaMemcpyDeviceToHost, e->stream[0]));
+        CKB(cudaStreamSynchronize(e->stream[0]));
+#undef CKB
+    } while (0);
+    cudaFree(d_st); cudaFree(d_nul); cudaFree(d_seen); cudaFree(d_out);
+    return rc;
+}
+
+static int ensure_skeleton(act_engine* e, int kind) {
+    if (kind < 0 || kind > 3) return fail_msg("bad record kind (0 request, 1 response, 2 proof, 3 refund)");
+    if (e->d_skel[kind]) return 0;
+    size_t len = act_cbor_len(kind);
+    std::vector<int32_t> h(len);
+    act_build_skeleton(h.data(), kind);
+    CK(cudaMalloc((void**)&e->d_skel[kind], len * 4));
+    CK(cudaMemcpy(e->d_skel[kind], h.data(), len * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int act_unpack_cbor_dev(act_engine* e, int kind, size_t n, const void* cbor, void* records, void* status, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!cbor || !records || !status) return fail_msg("act_unpack_cbor_dev: null buffer");
+    CK(cudaSetDevice(e->device));
+    int rc = ensure_skeleton(e, kind);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    unsigned grid = (unsigned)(n < 148 * 8 ? n : 148 * 8);
+    cbor_unpack_kernel<<<grid, 256, 0, st>>>(n, e->d_skel[kind], (u32)act_cbor_len(kind), (u32)act_rec_len(kind), (const u8*)cbor, (u8*)records, (u8*)status);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int act_encode_cbor_dev(act_engine* e, int kind, size_t n, const void* records, void* cbor, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!cbor || !records) return fail_msg("act_encode_cbor_dev: null buffer");
+    CK(cudaSetDevice(e->device));
+    int rc = ensure_skeleton(e, kind);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    size_t total = n * act_cbor_len(kind);
+    unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    cbor_encode_kernel<<<grid, 256, 0, st>>>(n, e->d_skel[kind], (u32)act_cbor_len(kind), (u32)act_rec_len(kind), (const u8*)records, (u8*)cbor);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+// host-buffer forms (one staging round trip; meant for ingest/egress next to the batch calls)
+static int cbor_host_roundtrip(act_engine* e, int kind, size_t n, const uint8_t* in, size_t in_rec, uint8_t* out, size_t out_rec, uint8_t* status, bool unpack) {
+    CK(cudaSetDevice(e->device));
+    u8 *d_in = nullptr, *d_out = nullptr, *d_st = nullptr;
+    int rc = 0;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaMalloc((void**)&d_in, n * in_rec)); CKB(cudaMalloc((void**)&d_out, n * out_rec));
+        if (unpack) CKB(cudaMalloc((void**)&d_st, n));
+        CKB(cudaMemcpyAsync(d_in, in, n * in_rec, cudaMemcpyHostToDevice, e->stream[0]));
+        rc = unpack ? act_unpack_cbor_dev(e, kind, n, d_in, d_out, d_st, e->stream[0]) : act_encode_cbor_dev(e, kind, n, d_in, d_out, e->stream[0]);
+        if (rc) break;
+        CKB(cudaMemcpyAsync(out, d_out, n * out_rec, cudaMemcpyDeviceToHost, e->stream[0]));
+        if (unpack) CKB(cudaMemcpyAsync(status, d_st, n, cudaMemcpyDeviceToHost, e->stream[0]));
+        CKB(cudaStreamSynchronize(e->stream[0]));
+#undef CKB
+    } while (0);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_st);
+    return rc;
+}
+extern "C" int act_unpack_cbor(act_engine* e, int kind, size_t n, const uint8_t* cbor, uint8_t* records, uint8_t* status) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (kind < 0 || kind > 3) return fail_msg("bad record kind");
+    if (!cbor || !records || !status) return fail_msg("act_unpack_cbor: null buffer");
+    return cbor_host_roundtrip(e, kind, n, cbor, act_cbor_len(kind), records, act_rec_len(kind), status, true);
+}
+extern "C" int act_encode_cbor(act_engine* e, int kind, size_t n, const uint8_t* records, uint8_t* cbor) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (kind < 0 || kind > 3) return fail_msg("bad record kind");
+    if (!cbor || !records) return fail_msg("act_encode_cbor: null buffer");
+    return cbor_host_roundtrip(e, kind, n, records, act_rec_len(kind), cbor, act_cbor_len(kind), nullptr, false);
 }

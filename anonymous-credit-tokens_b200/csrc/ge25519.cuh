@@ -24,6 +24,38 @@ ACT_FN ge_cached ge_to_cached(const ge& p) {
 }
 ACT_FN ge ge_neg(const ge& p) { ge r; r.X = fe_neg(p.X); r.Y = p.Y; r.Z = p.Z; r.T = fe_neg(p.T); return r; }
 
+// ---- ALU-pipe copies around the field-multiply calls ---------------------------------------------------------
+// ptxas marshals call arguments and results with IMAD.MOV, which runs on the integer-multiply pipe -- the pipe this
+// code is bound by.  An exclusive-or with a run-time zero that ptxas cannot fold is a copy that is guaranteed to run on the
+// ALU pipe (LOP3; an add would become IMAD.IADD), and the register allocator can then place its result directly in the argument registers.
+// ACT_ALU_COPY bit 0: copy arguments, bit 1: copy results.
+#ifndef ACT_ALU_COPY
+#define ACT_ALU_COPY 0
+#endif
+#if defined(__CUDACC__) && ACT_ALU_COPY
+__device__ u32 act_zero_word = 0;
+#endif
+#if ACT_PTX && ACT_ALU_COPY
+ACT_FN u32 act_zero() { return __ldg(&act_zero_word); }
+ACT_FN fe fe_cp(const fe& a, u32 z) {
+    fe r;
+    ACT_UNROLL for (int i = 0; i < 8; i++) asm("xor.b32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(z));
+    return r;
+}
+ACT_FN fe fe_mul_c(const fe& a, const fe& b, u32 z) {
+    fe r = (ACT_ALU_COPY & 1) ? fe_mul(fe_cp(a, z), fe_cp(b, z)) : fe_mul(a, b);
+    return (ACT_ALU_COPY & 2) ? fe_cp(r, z) : r;
+}
+ACT_FN fe fe_sq_c(const fe& a, u32 z) {
+    fe r = (ACT_ALU_COPY & 1) ? fe_sq(fe_cp(a, z)) : fe_sq(a);
+    return (ACT_ALU_COPY & 2) ? fe_cp(r, z) : r;
+}
+#else
+ACT_FN u32 act_zero() { return 0; }
+ACT_FN fe fe_mul_c(const fe& a, const fe& b, u32) { return fe_mul(a, b); }
+ACT_FN fe fe_sq_c(const fe& a, u32) { return fe_sq(a); }
+#endif
+
 // The three hot point operations.  ACT_GE_CALLS=1 makes THEM the call boundary (field multiplies inlined inside:
 // one round of argument moves per 7-8 multiplies).  Measured on B200 it is slower (90k vs 119k proofs/s): the
 // three bodies together no longer fit the instruction cache.  Default 0 = calls at the field-multiply level.
@@ -32,15 +64,16 @@ ACT_FN ge ge_neg(const ge& p) { ge r; r.X = fe_neg(p.X); r.Y = p.Y; r.Z = p.Z; r
 #endif
 #if ACT_GE_CALLS
 #define ACT_GE_FN ACT_NOINLINE
-#define GE_MUL fe_mul_inl
-#define GE_SQ fe_sq_inl
+#define GE_MUL(a, b) fe_mul_inl(a, b)
+#define GE_SQ(a) fe_sq_inl(a)
 #else
 #define ACT_GE_FN ACT_FN
-#define GE_MUL fe_mul
-#define GE_SQ fe_sq
+#define GE_MUL(a, b) fe_mul_c(a, b, zc_)
+#define GE_SQ(a) fe_sq_c(a, zc_)
 #endif
 // r = p + q, 8M
 ACT_GE_FN ge ge_add_cached(ge p, ge_cached q) {
+    u32 zc_ = act_zero(); (void)zc_;
     fe PP = GE_MUL(fe_add(p.Y, p.X), q.YpX);
     fe MM = GE_MUL(fe_sub(p.Y, p.X), q.YmX);
     fe TT = GE_MUL(p.T, q.T2d);
@@ -53,6 +86,7 @@ ACT_GE_FN ge ge_add_cached(ge p, ge_cached q) {
 }
 // r = p + q for affine-Niels q, 7M
 ACT_GE_FN ge ge_add_niels(ge p, ge_niels q) {
+    u32 zc_ = act_zero(); (void)zc_;
     fe PP = GE_MUL(fe_add(p.Y, p.X), q.ypx);
     fe MM = GE_MUL(fe_sub(p.Y, p.X), q.ymx);
     fe TT = GE_MUL(p.T, q.xy2d);
@@ -68,6 +102,7 @@ ACT_FN ge ge_sub(const ge& p, const ge& q) { return ge_add_cached(p, ge_to_cache
 // r = 2p.  T of the input is not read (4S + 4M; the T product is computed unconditionally in the call form
 // so that a single instance of the code serves every doubling).
 ACT_GE_FN ge ge_dbl_t(ge p) {
+    u32 zc_ = act_zero(); (void)zc_;
     fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y), ZZ = GE_SQ(p.Z);
     fe ZZ2 = fe_add(ZZ, ZZ);
     fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
@@ -79,6 +114,7 @@ ACT_GE_FN ge ge_dbl_t(ge p) {
 }
 // doubling without the T output (4S + 3M): p.T is carried through untouched and must not be used
 ACT_GE_FN ge ge_dbl_not(ge p) {
+    u32 zc_ = act_zero(); (void)zc_;
     fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y), ZZ = GE_SQ(p.Z);
     fe ZZ2 = fe_add(ZZ, ZZ);
     fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
@@ -94,15 +130,16 @@ ACT_FN ge ge_dbl(const ge& p, bool want_t) { return want_t ? ge_dbl_t(p) : ge_db
 // keeps the window loops small.  (Inlining the field multiplications into the point operations was measured on
 // B200: the 17-37 KB loop bodies miss the instruction cache and run 7-25 % slower than the call form, see DESIGN.md.)
 ACT_FN ge ge_dbl_u(const ge& p, bool want_t) {
-    fe XX = fe_sq(p.X), YY = fe_sq(p.Y), ZZ = fe_sq(p.Z);
+    u32 zc_ = act_zero(); (void)zc_;
+    fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y), ZZ = GE_SQ(p.Z);
     fe ZZ2 = fe_add(ZZ, ZZ);
-    fe XpY2 = fe_sq(fe_add(p.X, p.Y));
+    fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
     fe Yc = fe_add(YY, XX), Zc = fe_sub(YY, XX);
     fe Xc = fe_sub(XpY2, Yc), Tc = fe_sub(ZZ2, Zc);
     ge r;
-    r.X = fe_mul(Xc, Tc); r.Y = fe_mul(Yc, Zc); r.Z = fe_mul(Zc, Tc);
+    r.X = GE_MUL(Xc, Tc); r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Zc, Tc);
     r.T = p.T;
-    if (want_t) r.T = fe_mul(Xc, Yc);
+    if (want_t) r.T = GE_MUL(Xc, Yc);
     return r;
 }
 

@@ -38,15 +38,24 @@ def all_gather_results(status, nullifiers, n_total, group=None):
     return s, nl
 
 
-def flag_replays(status, nullifiers, seen=None):
+def flag_replays(status, nullifiers, seen=None, engine=None):
     """Caller-side double-spend screen over a gathered batch (the reference leaves this to the caller:
     src/lib.rs:741-745, examples/act.rs:65-69, src/tests.rs:28-50).  Among ACCEPTED proofs (status 0) the first
     occurrence of a nullifier in slice order keeps status 0; later ones -- and any nullifier present in `seen`
     (uint8[k*32] of previously spent nullifiers) -- are flagged 3 (DoubleSpendError).  Refund outputs are not
-    touched.  Returns a new status tensor."""
+    touched.  Returns a new status tensor.  With `engine` and CUDA tensors the engine's own kernel runs; the torch
+    formulation below serves CPU tensors (gloo tests) and is the semantic reference."""
     n = status.numel()
     if n == 0:
         return status.clone()
+    if engine is not None and status.is_cuda:
+        # the CUDA replay screen of the engine (act_flag_replays_dev: hash table of lowest index per key)
+        out = torch.empty_like(status)
+        status, nullifiers = status.contiguous(), nullifiers.contiguous()
+        k = 0 if seen is None else seen.numel() // 32
+        sp = seen.contiguous().data_ptr() if k else None
+        engine.flag_replays_dev(n, status.data_ptr(), nullifiers.data_ptr(), k, sp, out.data_ptr(), torch.cuda.current_stream(status.device).cuda_stream)
+        return out
     keys = nullifiers.view(n, 32).contiguous().view(torch.int64).view(n, 4)
     ok = status == 0
     if seen is not None and seen.numel():

@@ -141,6 +141,30 @@ ACT_API size_t act_encode_issuance_response_cbor(const uint8_t resp[160], uint8_
 ACT_API size_t act_encode_spend_proof_cbor(const uint8_t* proof /* 16832 */, uint8_t* out /* 18036 */);
 ACT_API size_t act_encode_refund_cbor(const uint8_t refund[128], uint8_t out[141]);
 
+/* ---- rows either side of the hot path ----
+ *
+ * Replay screen over a batch: what the reference leaves to the caller's nullifier database (src/lib.rs:741-745,
+ * examples/act.rs:65-69; semantics of NullifierDb in src/tests.rs:28-50 applied in slice order).  Among accepted
+ * proofs (status 0) the first occurrence of a nullifier keeps 0; every later one, and every nullifier present in
+ * seen[n_seen*32], becomes 3 (DoubleSpendError).  Other statuses are copied.  Refund outputs are not touched. */
+ACT_API int act_flag_replays_dev(act_engine* e, size_t n, const void* status, const void* nullifiers, size_t n_seen, const void* seen,
+                                 void* status_out, void* stream);
+ACT_API int act_flag_replays(act_engine* e, size_t n, const uint8_t* status, const uint8_t* nullifiers, size_t n_seen, const uint8_t* seen,
+                             uint8_t* status_out);
+/* Canonical-CBOR fast path on the device.  kind: 0 IssuanceRequest (141 B <-> 128 B), 1 IssuanceResponse (176 <-> 160),
+ * 2 SpendProof (18036 <-> 16832), 3 Refund (141 <-> 128).  Items are fixed-size and contiguous.  Unpack accepts exactly
+ * the encoding the reference's to_cbor produces (src/cbor.rs:96-103,153-161,216-268,413-420): status 0, or 0xFF =
+ * "not the canonical skeleton" -> hand that item to act_pack_*_cbor (the lenient host parser). */
+#define ACT_KIND_REQUEST 0
+#define ACT_KIND_RESPONSE 1
+#define ACT_KIND_PROOF 2
+#define ACT_KIND_REFUND 3
+#define ACT_STATUS_NOT_CANONICAL 0xFF
+ACT_API int act_unpack_cbor_dev(act_engine* e, int kind, size_t n, const void* cbor, void* records, void* status, void* stream);
+ACT_API int act_encode_cbor_dev(act_engine* e, int kind, size_t n, const void* records, void* cbor, void* stream);
+ACT_API int act_unpack_cbor(act_engine* e, int kind, size_t n, const uint8_t* cbor, uint8_t* records, uint8_t* status);
+ACT_API int act_encode_cbor(act_engine* e, int kind, size_t n, const uint8_t* records, uint8_t* cbor);
+
 #ifdef __cplusplus
 }
 #endif

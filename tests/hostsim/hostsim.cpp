@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../anonymous-credit-tokens_b200/csrc/act_device.cuh"
+#include "../../anonymous-credit-tokens_b200/csrc/act_aux.cuh"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -191,3 +192,23 @@ EXPORT int hs_encode_stage(const uint8_t* enc /* 256 x 32 */, uint8_t* out /* 25
     return 1;
 }
 EXPORT void hs_sc_half(const uint8_t a[32], uint8_t out[32]) { u32 w[8]; memcpy(w, a, 32); sc r = sc_half(sc_from_words(w)); memcpy(out, r.v, 32); }
+
+// canonical-CBOR skeletons of act_aux.cuh applied on the host (the device kernels do exactly this per byte)
+EXPORT int hs_cbor_skeleton_encode(int kind, const uint8_t* rec, uint8_t* out) {
+    size_t len = act_cbor_len(kind);
+    std::vector<int32_t> sk(len);
+    act_build_skeleton(sk.data(), kind);
+    for (size_t i = 0; i < len; i++) out[i] = sk[i] >= 0 ? rec[sk[i]] : (uint8_t)(-(sk[i] + 1));
+    return (int)len;
+}
+EXPORT int hs_cbor_skeleton_unpack(int kind, const uint8_t* cbor, uint8_t* rec) {
+    size_t len = act_cbor_len(kind);
+    std::vector<int32_t> sk(len);
+    act_build_skeleton(sk.data(), kind);
+    int bad = 0;
+    for (size_t i = 0; i < len; i++) {
+        if (sk[i] >= 0) rec[sk[i]] = cbor[i];
+        else if (cbor[i] != (uint8_t)(-(sk[i] + 1))) bad = 1;
+    }
+    return bad ? 0xFF : 0;
+}

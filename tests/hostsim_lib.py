@@ -48,6 +48,8 @@ def lib():
         L.hs_recode.argtypes = [vp, i32, vp]
         L.hs_encode_stage.argtypes = [vp, vp]; L.hs_encode_stage.restype = i32
         L.hs_sc_half.argtypes = [vp, vp]
+        L.hs_cbor_skeleton_encode.argtypes = [i32, vp, vp]; L.hs_cbor_skeleton_encode.restype = i32
+        L.hs_cbor_skeleton_unpack.argtypes = [i32, vp, vp]; L.hs_cbor_skeleton_unpack.restype = i32
         _lib = L
     return _lib
 
@@ -125,3 +127,15 @@ class Ctx:
         a, ap = _in(s); o, op = _out(32)
         lib().hs_scalarmult_base(self.p, base, ap, ct, op)
         return o.tobytes()
+
+
+def cbor_skeleton_encode(kind, rec, out_len):
+    a, ap = _in(rec); o, op = _out(out_len)
+    n = lib().hs_cbor_skeleton_encode(kind, ap, op)
+    return o[:n].tobytes()
+
+
+def cbor_skeleton_unpack(kind, cbor, rec_len):
+    a, ap = _in(cbor); o, op = _out(rec_len)
+    st = lib().hs_cbor_skeleton_unpack(kind, ap, op)
+    return o.tobytes(), st

@@ -147,3 +147,24 @@ def test_batched_double_and_encode_stage_with_identity_points():
         x = rnd.getrandbits(256)
         h = int.from_bytes(HS.call1("hs_sc_half", b32(x)), "little")
         assert h < ELL and (2 * h - x) % ELL == 0
+
+
+def test_cbor_skeletons_match_host_encoder_and_golden(act):
+    """The canonical skeletons the device fast path uses (act_aux.cuh) reproduce the host encoder byte for byte (which the
+    golden trip pins to ciborium's layout), invert it, and flag anything else as not canonical."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trip.json")))
+    recs = {0: bytes.fromhex(g["request"]), 1: bytes.fromhex(g["response"]), 2: bytes.fromhex(g["proof"]), 3: bytes.fromhex(g["refund"])}
+    enc = {0: act.encode_issuance_request_cbor, 1: act.encode_issuance_response_cbor, 2: act.encode_spend_proof_cbor, 3: act.encode_refund_cbor}
+    for kind, rec in recs.items():
+        want = enc[kind](rec)
+        got = HS.cbor_skeleton_encode(kind, rec, act.CBOR_BYTES[kind])
+        assert got == want and len(got) == act.CBOR_BYTES[kind]
+        back, st = HS.cbor_skeleton_unpack(kind, got, act.RECORD_BYTES[kind])
+        assert st == 0 and back == rec
+        bad = bytearray(got); bad[0] ^= 1                       # wrong map header
+        assert HS.cbor_skeleton_unpack(kind, bytes(bad), act.RECORD_BYTES[kind])[1] == 0xFF
+        bad = bytearray(got); bad[2] = 0x59                     # a bstr head that is not 58 20
+        assert HS.cbor_skeleton_unpack(kind, bytes(bad), act.RECORD_BYTES[kind])[1] == 0xFF
+    assert HS.cbor_skeleton_encode(0, recs[0], 141).hex() == g["cbor_request"]
+    assert HS.cbor_skeleton_encode(3, recs[3], 141).hex() == g["cbor_refund"]
