@@ -31,6 +31,9 @@ KIND_REQUEST, KIND_RESPONSE, KIND_PROOF, KIND_REFUND = 0, 1, 2, 3
 CBOR_BYTES = {0: 141, 1: 176, 2: 18036, 3: 141}
 RECORD_BYTES = {0: 128, 1: 160, 2: 16832, 3: 128}
 NOT_CANONICAL = 0xFF
+TOKEN_BYTES = 160
+PREREFUND_BYTES = 96
+PROVE_RND_BYTES = 524 * 64
 
 # status codes (include/act_engine.h; 1 + discriminant of the reference's `Error`, src/lib.rs:102-112)
 OK = 0
@@ -66,6 +69,7 @@ EXPORTED_SYMBOLS = [
     "act_pack_refunds_cbor", "act_encode_issuance_request_cbor", "act_encode_issuance_response_cbor",
     "act_encode_spend_proof_cbor", "act_encode_refund_cbor",
     "act_flag_replays", "act_flag_replays_dev", "act_unpack_cbor", "act_unpack_cbor_dev", "act_encode_cbor", "act_encode_cbor_dev",
+    "act_batch_request", "act_batch_request_dev", "act_batch_prove_spend", "act_batch_prove_spend_dev",
 ]
 
 
@@ -118,6 +122,10 @@ def load_library():
     lib.act_encode_cbor_dev.argtypes = [vp, i32, sz, vp, vp, vp]; lib.act_encode_cbor_dev.restype = i32
     lib.act_unpack_cbor.argtypes = [vp, i32, sz, vp, vp, vp]; lib.act_unpack_cbor.restype = i32
     lib.act_encode_cbor.argtypes = [vp, i32, sz, vp, vp]; lib.act_encode_cbor.restype = i32
+    lib.act_batch_request_dev.argtypes = [vp, sz, vp, vp, vp, vp]; lib.act_batch_request_dev.restype = i32
+    lib.act_batch_request.argtypes = [vp, sz, vp, vp, vp]; lib.act_batch_request.restype = i32
+    lib.act_batch_prove_spend_dev.argtypes = [vp, sz, vp, vp, vp, vp, u64, vp, vp, vp, vp]; lib.act_batch_prove_spend_dev.restype = i32
+    lib.act_batch_prove_spend.argtypes = [vp, sz, vp, vp, vp, vp, u64, vp, vp, vp]; lib.act_batch_prove_spend.restype = i32
     _lib = lib
     return lib
 
@@ -270,6 +278,37 @@ class Engine:
         st = np.zeros(n, np.uint8)
         _check(self.lib.act_batch_refund_check(self._h, n, cm.ctypes.data, rf.ctypes.data, st.ctypes.data), "act_batch_refund_check")
         return st
+
+    # ---- client-side batch generators (fixture grade, not constant time) ----
+    def batch_request(self, pre, rnd):
+        """n x PreIssuance::request (src/lib.rs:463-487).  pre n*64 (r|k), rnd n*128 (k'_wide|r'_wide) -> requests n*128."""
+        p = _u8(pre); n = p.size // 64
+        r = _u8(rnd, n * RND_BYTES, "rnd")
+        req = np.zeros(n * REQUEST_BYTES, np.uint8)
+        _check(self.lib.act_batch_request(self._h, n, p.ctypes.data, r.ctypes.data, req.ctypes.data), "act_batch_request")
+        return req
+
+    def batch_prove_spend(self, tokens, charges, rnd=None, seed=None, first_index=0):
+        """n x CreditToken::prove_spend (src/lib.rs:972-1152).  tokens n*160 (A|e|k|r|c), charges n*32; rnd n*33536 explicit
+        RNG bytes in the reference's order, or seed (32 bytes) for the BLAKE3-XOF derived stream.
+        Returns (proofs n*16832, prerefunds n*96 (k*|r*|m), status n)."""
+        tk = _u8(tokens); n = tk.size // TOKEN_BYTES
+        ch = _u8(charges, n * 32, "charges")
+        r = _u8(rnd, n * PROVE_RND_BYTES, "rnd") if rnd is not None else None
+        sd = _u8(seed, 32, "seed") if seed is not None else None
+        proofs = np.zeros(n * PROOF_BYTES, np.uint8); pr = np.zeros(n * PREREFUND_BYTES, np.uint8); st = np.zeros(n, np.uint8)
+        _check(self.lib.act_batch_prove_spend(self._h, n, tk.ctypes.data, ch.ctypes.data, r.ctypes.data if r is not None else None,
+                                              sd.ctypes.data if sd is not None else None, first_index, proofs.ctypes.data, pr.ctypes.data, st.ctypes.data),
+               "act_batch_prove_spend")
+        return proofs, pr, st
+
+    def batch_request_dev(self, n, pre, rnd, req, stream=0):
+        _check(self.lib.act_batch_request_dev(self._h, n, pre, rnd, req, stream), "act_batch_request_dev")
+
+    def batch_prove_spend_dev(self, n, tokens, charges, rnd, seed, first_index, proofs, prerefunds, status, stream=0):
+        sd = _u8(seed, 32, "seed") if seed is not None else None
+        _check(self.lib.act_batch_prove_spend_dev(self._h, n, tokens, charges, rnd, sd.ctypes.data if sd is not None else None, first_index,
+                                                  proofs, prerefunds, status, stream), "act_batch_prove_spend_dev")
 
     # ---- rows either side of the hot path ----
     def flag_replays(self, status, nullifiers, seen=None):

@@ -502,10 +502,11 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
 // Writes items 133 .. 388.
 // =============================================================================================================
 #define ACT_ENC_BATCH 16
-ACT_FN void spend_encode_thread(const act_ctx* C, size_t p, int part, const u32* cpts, u32* items) {
+// pts = points per proof in cpts (256 for the verifier: items 133..388; 384 for the prover: items 5..388), item0 = first item
+ACT_FN void spend_encode_thread(const act_ctx* C, size_t p, int part, const u32* cpts, u32* items, int pts = 2 * ACT_L, int item0 = 133) {
     (void)C;
-    const u32* src = cpts + ((size_t)2 * ACT_L * p + (size_t)part * ACT_ENC_BATCH) * 32;
-    u32* dst = items + (size_t)ACT_ITEM_WORDS * p + 8 * (133 + part * ACT_ENC_BATCH);
+    const u32* src = cpts + ((size_t)pts * p + (size_t)part * ACT_ENC_BATCH) * 32;
+    u32* dst = items + (size_t)ACT_ITEM_WORDS * p + 8 * (item0 + part * ACT_ENC_BATCH);
     fe prefix[ACT_ENC_BATCH];
     fe acc = fe_one();
     ACT_NOUNROLL for (int i = 0; i < ACT_ENC_BATCH; i++) {

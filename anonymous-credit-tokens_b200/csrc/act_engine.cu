@@ -16,6 +16,7 @@
 #include "../../include/act_engine.h"
 #include "act_device.cuh"
 #include "act_aux.cuh"
+#include "act_prove.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // kernels: thin index wrappers around the per-thread bodies in act_device.cuh
@@ -46,9 +47,30 @@ __global__ void __launch_bounds__(ACT_L, ACT_RANGE_BLOCKS_PER_SM) spend_range_ke
 // encodes the 256 commitments of each proof: one thread per 16 points (batched inversion)
 #define ACT_ENC_BLOCK 128
 #define ACT_ENC_PARTS (2 * ACT_L / ACT_ENC_BATCH)
-__global__ void __launch_bounds__(ACT_ENC_BLOCK, 4) spend_encode_kernel(const act_ctx* C, size_t m, const u32* cpts, u32* items) {
+__global__ void __launch_bounds__(ACT_ENC_BLOCK, 4) spend_encode_kernel(const act_ctx* C, size_t m, const u32* cpts, u32* items, int pts, int item0) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < m * ACT_ENC_PARTS) spend_encode_thread(C, t / ACT_ENC_PARTS, (int)(t % ACT_ENC_PARTS), cpts, items);
+    int parts = pts / ACT_ENC_BATCH;
+    if (t < m * parts) spend_encode_thread(C, t / parts, (int)(t % parts), cpts, items, pts, item0);
+}
+// ---- client-side generators (act_prove.cuh) ----
+__global__ void __launch_bounds__(ACT_L, 4) prove_range_kernel(const act_ctx* C, prove_rng R, size_t m, const u32* tokens, const u32* charges, u32* cpts) {
+    for (size_t p = blockIdx.x; p < m; p += gridDim.x) prove_range_thread(C, &R, p, p, threadIdx.x, tokens, charges, cpts);
+}
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK, 8) prove_head_kernel(const act_ctx* C, prove_rng R, size_t m, const u32* tokens, u32* items, u32* aux, u8* status) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) prove_head_thread(C, &R, p, p, tokens, items, aux, status);
+}
+__global__ void __launch_bounds__(ACT_HASH_BLOCK) prove_challenge_kernel(size_t m, u32* cvs, u32* gammas) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) prove_challenge_thread(p, cvs, gammas);
+}
+__global__ void __launch_bounds__(ACT_L, 4) prove_finish_kernel(const act_ctx* C, prove_rng R, size_t m, const u32* tokens, const u32* charges, const u32* items,
+                                                               const u32* aux, const u32* gammas, const u8* status, u32* proofs, u32* prerefunds) {
+    for (size_t p = blockIdx.x; p < m; p += gridDim.x) prove_finish_thread(C, &R, p, p, threadIdx.x, tokens, charges, items, aux, gammas, status, proofs, prerefunds);
+}
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) request_kernel(const act_ctx* C, size_t n, const u32* pre, const u32* rnd, u32* req) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) request_thread(C, i, pre, rnd, req);
 }
 __global__ void __launch_bounds__(ACT_HEAD_BLOCK, 8) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,6 +225,8 @@ struct act_engine {
     uint64_t launches = 0;
     int32_t* d_skel[4] = {nullptr, nullptr, nullptr, nullptr};   // canonical CBOR skeletons (request, response, proof, refund)
     u32* d_rp_table = nullptr; size_t rp_cap = 0;                 // replay-screen hash table
+    // prover scratch (one chunk): transcript items, half-points, chunk CVs, challenges, r3
+    u32 *pv_items = nullptr, *pv_cpts = nullptr, *pv_cvs = nullptr, *pv_gammas = nullptr, *pv_aux = nullptr; size_t pv_cap = 0;
     // optional per-kernel device timing (CUDA events on the launching stream)
     bool timing = false;
     struct timed { int kind; cudaEvent_t a, b; };
@@ -304,6 +328,7 @@ extern "C" void act_engine_destroy(act_engine* e) {
     cudaFree(e->d_tables); cudaFree(e->d_bases);
     for (int k = 0; k < 4; k++) cudaFree(e->d_skel[k]);
     cudaFree(e->d_rp_table);
+    cudaFree(e->pv_items); cudaFree(e->pv_cpts); cudaFree(e->pv_cvs); cudaFree(e->pv_gammas); cudaFree(e->pv_aux);
     if (e->fork) cudaEventDestroy(e->fork);
     for (int s = 0; s < 2; s++) if (e->join[s]) cudaEventDestroy(e->join[s]);
     for (int s = 0; s < 2; s++) {
@@ -535,7 +560,7 @@ static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, 
     CK(cudaMemsetAsync(s->flags, 0, m * 4, st));
     unsigned rgrid = m < s->range_grid ? (unsigned)m : s->range_grid;
     LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<rgrid, ACT_L, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->flags, s->tabs, s->cpts)));
-    LAUNCH(e, K_ENCODE, st, (spend_encode_kernel<<<nblocks(m * ACT_ENC_PARTS, ACT_ENC_BLOCK), ACT_ENC_BLOCK, 0, st>>>(e->d_ctx, m, s->cpts, s->items)));
+    LAUNCH(e, K_ENCODE, st, (spend_encode_kernel<<<nblocks(m * ACT_ENC_PARTS, ACT_ENC_BLOCK), ACT_ENC_BLOCK, 0, st>>>(e->d_ctx, m, s->cpts, s->items, 2 * ACT_L, 133)));
     LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->kprime, s->flags)));
     LAUNCH(e, K_CHUNK, st, (spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, s->items, s->cvs)));
     LAUNCH(e, K_FINISH, st, (spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status)));
@@ -779,4 +804,110 @@ extern "C" int act_encode_cbor(act_engine* e, int kind, size_t n, const uint8_t*
     if (kind < 0 || kind > 3) return fail_msg("bad record kind");
     if (!cbor || !records) return fail_msg("act_encode_cbor: null buffer");
     return cbor_host_roundtrip(e, kind, n, records, act_rec_len(kind), cbor, act_cbor_len(kind), nullptr, false);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// client-side batch generators (act_prove.cuh): PreIssuance::request and CreditToken::prove_spend
+// ---------------------------------------------------------------------------------------------------
+#define ACT_PROVE_CHUNK 8192
+extern "C" int act_batch_request_dev(act_engine* e, size_t n, const void* pre, const void* rnd, void* req, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!pre || !rnd || !req) return fail_msg("act_batch_request_dev: null buffer");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    request_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)pre, (const u32*)rnd, (u32*)req);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int act_batch_prove_spend_dev(act_engine* e, size_t n, const void* tokens, const void* charges, const void* rnd, const uint8_t seed[32],
+                                         uint64_t first_index, void* proofs, void* prerefunds, void* status, void* stream) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!tokens || !charges || !proofs || !prerefunds || !status || (!rnd && !seed)) return fail_msg("act_batch_prove_spend_dev: null buffer");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
+    size_t cap = n < ACT_PROVE_CHUNK ? n : ACT_PROVE_CHUNK;
+    if (e->pv_cap < cap) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(e->pv_items); cudaFree(e->pv_cpts); cudaFree(e->pv_cvs); cudaFree(e->pv_gammas); cudaFree(e->pv_aux);
+        e->pv_items = e->pv_cpts = e->pv_cvs = e->pv_gammas = e->pv_aux = nullptr; e->pv_cap = 0;
+        CK(cudaMalloc((void**)&e->pv_items, cap * ACT_ITEM_WORDS * 4));
+        CK(cudaMalloc((void**)&e->pv_cpts, cap * ACT_PROVE_PTS * 128));
+        CK(cudaMalloc((void**)&e->pv_cvs, cap * ACT_SPEND_CHUNKS * 32));
+        CK(cudaMalloc((void**)&e->pv_gammas, cap * 32));
+        CK(cudaMalloc((void**)&e->pv_aux, cap * 32));
+        e->pv_cap = cap;
+    }
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    for (size_t off = 0; off < n; off += ACT_PROVE_CHUNK) {
+        size_t m = n - off < ACT_PROVE_CHUNK ? n - off : ACT_PROVE_CHUNK;
+        prove_rng R;
+        memset(&R, 0, sizeof R);
+        R.rnd = rnd ? (const u32*)rnd + off * ACT_PROVE_SCALARS * 16 : nullptr;
+        if (seed) memcpy(R.seed, seed, 32);
+        R.first_index = first_index + off;
+        const u32* tk = (const u32*)tokens + off * 40;
+        const u32* ch = (const u32*)charges + off * 8;
+        u8* stt = (u8*)status + off;
+        unsigned grid = (unsigned)(m < (size_t)sms * 4 ? m : (size_t)sms * 4);
+        prove_range_kernel<<<grid, ACT_L, 0, st>>>(e->d_ctx, R, m, tk, ch, e->pv_cpts);
+        spend_encode_kernel<<<nblocks(m * ACT_PROVE_PARTS, ACT_ENC_BLOCK), ACT_ENC_BLOCK, 0, st>>>(e->d_ctx, m, e->pv_cpts, e->pv_items, ACT_PROVE_PTS, 5);
+        prove_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, R, m, tk, e->pv_items, e->pv_aux, stt);
+        spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, e->pv_items, e->pv_cvs);
+        prove_challenge_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(m, e->pv_cvs, e->pv_gammas);
+        prove_finish_kernel<<<grid, ACT_L, 0, st>>>(e->d_ctx, R, m, tk, ch, e->pv_items, e->pv_aux, e->pv_gammas, stt,
+                                                   (u32*)proofs + off * ACT_PROOF_WORDS, (u32*)prerefunds + off * 24);
+        e->launches += 6;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+// host-buffer forms
+extern "C" int act_batch_request(act_engine* e, size_t n, const uint8_t* pre, const uint8_t* rnd, uint8_t* req) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!pre || !rnd || !req) return fail_msg("act_batch_request: null buffer");
+    CK(cudaSetDevice(e->device));
+    u8 *d_pre = nullptr, *d_rnd = nullptr, *d_req = nullptr;
+    int rc = 0;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaMalloc((void**)&d_pre, n * 64)); CKB(cudaMalloc((void**)&d_rnd, n * 128)); CKB(cudaMalloc((void**)&d_req, n * 128));
+        CKB(cudaMemcpyAsync(d_pre, pre, n * 64, cudaMemcpyHostToDevice, e->stream[0]));
+        CKB(cudaMemcpyAsync(d_rnd, rnd, n * 128, cudaMemcpyHostToDevice, e->stream[0]));
+        if ((rc = act_batch_request_dev(e, n, d_pre, d_rnd, d_req, e->stream[0]))) break;
+        CKB(cudaMemcpyAsync(req, d_req, n * 128, cudaMemcpyDeviceToHost, e->stream[0]));
+        CKB(cudaStreamSynchronize(e->stream[0]));
+#undef CKB
+    } while (0);
+    cudaFree(d_pre); cudaFree(d_rnd); cudaFree(d_req);
+    return rc;
+}
+extern "C" int act_batch_prove_spend(act_engine* e, size_t n, const uint8_t* tokens, const uint8_t* charges, const uint8_t* rnd, const uint8_t seed[32],
+                                     uint64_t first_index, uint8_t* proofs, uint8_t* prerefunds, uint8_t* status) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!tokens || !charges || !proofs || !prerefunds || !status || (!rnd && !seed)) return fail_msg("act_batch_prove_spend: null buffer");
+    CK(cudaSetDevice(e->device));
+    u8 *d_tk = nullptr, *d_ch = nullptr, *d_rnd = nullptr, *d_pf = nullptr, *d_pr = nullptr, *d_st = nullptr;
+    int rc = 0;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaMalloc((void**)&d_tk, n * 160)); CKB(cudaMalloc((void**)&d_ch, n * 32)); CKB(cudaMalloc((void**)&d_pf, n * ACT_PROOF_BYTES));
+        CKB(cudaMalloc((void**)&d_pr, n * 96)); CKB(cudaMalloc((void**)&d_st, n));
+        if (rnd) { CKB(cudaMalloc((void**)&d_rnd, n * ACT_PROVE_SCALARS * 64)); CKB(cudaMemcpyAsync(d_rnd, rnd, n * ACT_PROVE_SCALARS * 64, cudaMemcpyHostToDevice, e->stream[0])); }
+        CKB(cudaMemcpyAsync(d_tk, tokens, n * 160, cudaMemcpyHostToDevice, e->stream[0]));
+        CKB(cudaMemcpyAsync(d_ch, charges, n * 32, cudaMemcpyHostToDevice, e->stream[0]));
+        if ((rc = act_batch_prove_spend_dev(e, n, d_tk, d_ch, d_rnd, seed, first_index, d_pf, d_pr, d_st, e->stream[0]))) break;
+        CKB(cudaMemcpyAsync(proofs, d_pf, n * ACT_PROOF_BYTES, cudaMemcpyDeviceToHost, e->stream[0]));
+        CKB(cudaMemcpyAsync(prerefunds, d_pr, n * 96, cudaMemcpyDeviceToHost, e->stream[0]));
+        CKB(cudaMemcpyAsync(status, d_st, n, cudaMemcpyDeviceToHost, e->stream[0]));
+        CKB(cudaStreamSynchronize(e->stream[0]));
+#undef CKB
+    } while (0);
+    cudaFree(d_tk); cudaFree(d_ch); cudaFree(d_rnd); cudaFree(d_pf); cudaFree(d_pr); cudaFree(d_st);
+    return rc;
 }

@@ -165,6 +165,30 @@ ACT_API int act_encode_cbor_dev(act_engine* e, int kind, size_t n, const void* r
 ACT_API int act_unpack_cbor(act_engine* e, int kind, size_t n, const uint8_t* cbor, uint8_t* records, uint8_t* status);
 ACT_API int act_encode_cbor(act_engine* e, int kind, size_t n, const uint8_t* records, uint8_t* cbor);
 
+/* Client-side batch generators, bit-exact with the reference's prover for the same RNG bytes but NOT
+ * constant time: they exist to synthesise full-size batches of valid, unique fixtures on the device.
+ *   act_batch_request      = n x PreIssuance::request          src/lib.rs:463-487
+ *       pre  n*64  : r | k  (the PreIssuance scalars, reduced mod l on the device)
+ *       rnd  n*128 : the 64 bytes Scalar::random draws for k', then the 64 for r'   (:468-469)
+ *       req  n*128 : IssuanceRequest records
+ *   act_batch_prove_spend  = n x CreditToken::prove_spend      src/lib.rs:972-1152
+ *       tokens n*160 : A | e | k | r | c  (CreditToken);  charges n*32 : s
+ *       rnd    n*33536 : the 524 x 64 bytes the prover draws, in the reference's order (:978-984, 998-999, 1010-1023,
+ *                1057-1058); or NULL, then scalar t of proof i is the wide reduction of output block t of
+ *                BLAKE3-XOF(seed[32] || u64le(first_index + i))
+ *       proofs n*16832 : SpendProof records;  prerefunds n*96 : k* | r* | m  (PreRefund, :1124-1128)
+ *       status n : 0, or 0x81 when the token's A does not decode (outputs zero-filled)
+ *   Precondition as in the reference (:931-934): 2^128 > c >= s, otherwise the proof is produced but does not verify. */
+#define ACT_TOKEN_BYTES 160
+#define ACT_PREREFUND_BYTES 96
+#define ACT_PROVE_RND_BYTES 33536
+ACT_API int act_batch_request_dev(act_engine* e, size_t n, const void* pre, const void* rnd, void* req, void* stream);
+ACT_API int act_batch_request(act_engine* e, size_t n, const uint8_t* pre, const uint8_t* rnd, uint8_t* req);
+ACT_API int act_batch_prove_spend_dev(act_engine* e, size_t n, const void* tokens, const void* charges, const void* rnd, const uint8_t seed[32],
+                                      uint64_t first_index, void* proofs, void* prerefunds, void* status, void* stream);
+ACT_API int act_batch_prove_spend(act_engine* e, size_t n, const uint8_t* tokens, const uint8_t* charges, const uint8_t* rnd, const uint8_t seed[32],
+                                  uint64_t first_index, uint8_t* proofs, uint8_t* prerefunds, uint8_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,3 +167,34 @@ def overspend_proofs(ctx, n, seed=b"overspend"):
     out = ctx.generate(seeds, cr, ch, threads=min(os.cpu_count() or 1, 16))
     out["rnd"] = np.frombuffer(xof(seed + b"/rnd", 128 * n), dtype=np.uint8).copy()
     return out
+
+
+def trip_streams(seed, n):
+    """The per-trip randomness gen_valid(seed=...) hands to the oracle (oracle/act_oracle.c gen_worker): for trip i the
+    stream BLAKE3-XOF(seeds_i) gives PreIssuance (r, k), the request's 128 bytes, issue's 128 and prove_spend's 33 536.
+    Returns dict(pre n*64 [r|k reduced], req_rnd n*128, issue_rnd n*128, prove_rnd n*33536)."""
+    seeds = xof(seed + b"/seeds", 64 * n)
+    pre, rq, isr, pv = [], [], [], []
+    for i in range(n):
+        st = O.blake3(seeds[64 * i:64 * i + 64], 64 * 530)
+        pre.append(O.sc_reduce64(st[0:64]) + O.sc_reduce64(st[64:128])); rq.append(st[128:256]); isr.append(st[256:384]); pv.append(st[384:])
+    f = lambda parts: np.frombuffer(b"".join(parts), np.uint8).copy()
+    return dict(pre=f(pre), req_rnd=f(rq), issue_rnd=f(isr), prove_rnd=f(pv))
+
+
+def tokens_from(base, pre):
+    """CreditToken records (A | e | k | r | c, 160 B) of the trips in a gen_valid() corpus (src/lib.rs:555-561);
+    pre = trip_streams(...)["pre"]."""
+    n = len(base["resp"]) // 160
+    resp = base["resp"].reshape(n, 160); pr = pre.reshape(n, 64); cs = base["cs"].reshape(n, 32)
+    return np.concatenate([resp[:, :64], pr[:, 32:64], pr[:, :32], cs], axis=1).reshape(-1).copy()
+
+
+def charges_from(base):
+    return np.frombuffer(b"".join(int(c).to_bytes(32, "little") for c in base["charges"]), np.uint8).copy()
+
+
+def prover_stream(seed32: bytes, index: int) -> bytes:
+    """The derived RNG stream of act_batch_prove_spend: BLAKE3-XOF(seed || u64le(index)), 524 x 64 bytes."""
+    import blake3
+    return blake3.blake3(bytes(seed32) + int(index).to_bytes(8, "little")).digest(length=524 * 64)

@@ -13,6 +13,7 @@
 
 #include "../../anonymous-credit-tokens_b200/csrc/act_device.cuh"
 #include "../../anonymous-credit-tokens_b200/csrc/act_aux.cuh"
+#include "../../anonymous-credit-tokens_b200/csrc/act_prove.cuh"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -211,4 +212,37 @@ EXPORT int hs_cbor_skeleton_unpack(int kind, const uint8_t* cbor, uint8_t* rec) 
         else if (cbor[i] != (uint8_t)(-(sk[i] + 1))) bad = 1;
     }
     return bad ? 0xFF : 0;
+}
+
+// client-side generators (act_prove.cuh), the kernel bodies run in plain loops
+EXPORT void hs_request(const hs_ctx* H, size_t n, const uint8_t* pre, const uint8_t* rnd, uint8_t* req) {
+    auto p = to_words(pre, n * 64), r = to_words(rnd, n * 128);
+    std::vector<u32> out(n * 32 + 8);
+    for (size_t i = 0; i < n; i++) request_thread(&H->c, i, p.data(), r.data(), out.data());
+    memcpy(req, out.data(), n * 128);
+}
+EXPORT void hs_prove_spend(const hs_ctx* H, size_t n, const uint8_t* tokens, const uint8_t* charges, const uint8_t* rnd, const uint8_t* seed,
+                           uint64_t first_index, uint8_t* proofs, uint8_t* prerefunds, uint8_t* status) {
+    auto tk = to_words(tokens, n * 160), ch = to_words(charges, n * 32);
+    std::vector<u32> rw;
+    if (rnd) rw = to_words(rnd, n * (size_t)ACT_PROVE_SCALARS * 64);
+    prove_rng R;
+    memset(&R, 0, sizeof R);
+    R.rnd = rnd ? rw.data() : nullptr;
+    if (seed) memcpy(R.seed, seed, 32);
+    R.first_index = first_index;
+    std::vector<u32> cpts(n * ACT_PROVE_PTS * 32 + 8), items(n * ACT_ITEM_WORDS + 8), cvs(n * ACT_SPEND_CHUNKS * 8 + 8), gam(n * 8 + 8), aux(n * 8 + 8);
+    std::vector<u32> pf(n * ACT_PROOF_WORDS + 8), pr(n * 24 + 8);
+    for (size_t p = 0; p < n; p++)
+        for (int j = 0; j < ACT_L; j++) prove_range_thread(&H->c, &R, p, p, j, tk.data(), ch.data(), cpts.data());
+    for (size_t p = 0; p < n; p++)
+        for (int part = 0; part < ACT_PROVE_PARTS; part++) spend_encode_thread(&H->c, p, part, cpts.data(), items.data(), ACT_PROVE_PTS, 5);
+    for (size_t p = 0; p < n; p++) prove_head_thread(&H->c, &R, p, p, tk.data(), items.data(), aux.data(), status);
+    for (size_t p = 0; p < n; p++)
+        for (int c = 0; c < ACT_SPEND_CHUNKS; c++) spend_chunk_thread(&H->c, p, c, items.data(), cvs.data());
+    for (size_t p = 0; p < n; p++) prove_challenge_thread(p, cvs.data(), gam.data());
+    for (size_t p = 0; p < n; p++)
+        for (int j = 0; j < ACT_L; j++) prove_finish_thread(&H->c, &R, p, p, j, tk.data(), ch.data(), items.data(), aux.data(), gam.data(), status, pf.data(), pr.data());
+    memcpy(proofs, pf.data(), n * (size_t)ACT_PROOF_WORDS * 4);
+    memcpy(prerefunds, pr.data(), n * 96);
 }

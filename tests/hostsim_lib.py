@@ -48,6 +48,8 @@ def lib():
         L.hs_recode.argtypes = [vp, i32, vp]
         L.hs_encode_stage.argtypes = [vp, vp]; L.hs_encode_stage.restype = i32
         L.hs_sc_half.argtypes = [vp, vp]
+        L.hs_request.argtypes = [vp, sz, vp, vp, vp]
+        L.hs_prove_spend.argtypes = [vp, sz, vp, vp, vp, vp, C.c_uint64, vp, vp, vp]
         L.hs_cbor_skeleton_encode.argtypes = [i32, vp, vp]; L.hs_cbor_skeleton_encode.restype = i32
         L.hs_cbor_skeleton_unpack.argtypes = [i32, vp, vp]; L.hs_cbor_skeleton_unpack.restype = i32
         _lib = L
@@ -122,6 +124,21 @@ class Ctx:
         a, ap = _in(com); b, bp = _in(refund); s, sp = _out(n)
         lib().hs_refund_check(self.p, n, ap, bp, sp)
         return s
+
+    def request(self, pre, rnd):
+        n = len(pre) // 64
+        a, ap = _in(pre); b, bp = _in(rnd); o, op = _out(n * 128)
+        lib().hs_request(self.p, n, ap, bp, op)
+        return o
+
+    def prove_spend(self, tokens, charges, rnd=None, seed=None, first_index=0):
+        n = len(tokens) // 160
+        a, ap = _in(tokens); b, bp = _in(charges)
+        r, rp = _in(rnd) if rnd is not None else (None, None)
+        sd, sdp = _in(seed) if seed is not None else (None, None)
+        o, op = _out(n * PROOF_BYTES); q, qp = _out(n * 96); s, sp = _out(n)
+        lib().hs_prove_spend(self.p, n, ap, bp, rp, sdp, first_index, op, qp, sp)
+        return o, q, s
 
     def scalarmult_base(self, base, s, ct=0):
         a, ap = _in(s); o, op = _out(32)

@@ -266,3 +266,68 @@ def test_cbor_fast_path_on_device(act, engine, octx, base):
         assert (st == 0).all() and (back == recs).all()
     r0 = base["resp"][:160]
     assert engine.encode_cbor(act.KIND_RESPONSE, r0).tobytes() == act.encode_issuance_response_cbor(r0)
+
+
+def test_client_generators_on_gpu(act, engine, octx):
+    """request / prove_spend kernels: bit-exact with the oracle prover on identical RNG bytes; then a full-device trip at a
+    size no CPU prover reaches in test time: 20 000 unique tokens are requested, issued, spent and refunded on the GPU and
+    every stage accepts (issue -> issuance_check -> prove_spend -> verify+refund -> refund_check), nullifiers all distinct."""
+    import torch
+    n = 12
+    base = corpus.gen_valid(octx, n, seed=b"prover-gpu", threads=4)
+    st = corpus.trip_streams(b"prover-gpu", n)
+    assert (engine.batch_request(st["pre"], st["req_rnd"]) == base["req"]).all()
+    tokens, charges = corpus.tokens_from(base, st["pre"]), corpus.charges_from(base)
+    proofs, prer, status = engine.batch_prove_spend(tokens, charges, rnd=st["prove_rnd"])
+    assert (status == 0).all() and (proofs == base["proofs"]).all() and (prer == base["prerefund"]).all()
+    seed = corpus.xof(b"derived-seed", 32)
+    rnd = np.frombuffer(b"".join(corpus.prover_stream(seed, 1000 + i) for i in range(n)), np.uint8)
+    p1, r1, s1 = engine.batch_prove_spend(tokens, charges, seed=seed, first_index=1000)
+    p2, r2, s2 = engine.batch_prove_spend(tokens, charges, rnd=rnd)
+    assert (p1 == p2).all() and (r1 == r2).all() and (s1 == 0).all()
+    # full-device trip: torch ops and engine launches share one (non-default) stream
+    S = torch.cuda.Stream()
+    with torch.cuda.stream(S):
+        N = 20000
+        g = torch.Generator(device="cuda"); g.manual_seed(7)
+        rb = lambda k: torch.randint(0, 256, (k,), dtype=torch.uint8, device="cuda", generator=g)
+        pre = rb(N * 64); pre.view(N, 64)[:, 31] &= 0x0f; pre.view(N, 64)[:, 63] &= 0x0f            # r, k < 2^252 (already reduced)
+        req = torch.zeros(N * 128, dtype=torch.uint8, device="cuda")
+        engine.batch_request_dev(N, pre.data_ptr(), rb(N * 128).data_ptr(), req.data_ptr(), S.cuda_stream)
+        credits = torch.randint(20, 1000, (N,), device="cuda", generator=g)
+        spend = (torch.rand(N, device="cuda", generator=g) * (credits - 1)).long() + 1                # 1 <= s <= c - 1
+        le32 = lambda v: torch.cat([(v.view(N, 1) >> (8 * torch.arange(2, device="cuda"))).to(torch.uint8) & 0xff, torch.zeros(N, 30, dtype=torch.uint8, device="cuda")], 1).reshape(-1)
+        cs, ch = le32(credits), le32(spend)
+        resp = torch.zeros(N * 160, dtype=torch.uint8, device="cuda"); ist = torch.full((N,), 9, dtype=torch.uint8, device="cuda")
+        engine.batch_issue_dev(N, req.data_ptr(), cs.data_ptr(), rb(N * 128).data_ptr(), resp.data_ptr(), ist.data_ptr(), S.cuda_stream)
+        S.synchronize()
+        assert (ist == 0).all()
+        K = req.view(N, 128)[:, :32].contiguous()
+        cst = torch.full((N,), 9, dtype=torch.uint8, device="cuda")
+        engine.batch_issuance_check_dev(N, K.data_ptr(), resp.data_ptr(), cst.data_ptr(), S.cuda_stream)
+        tok = torch.cat([resp.view(N, 160)[:, :64], pre.view(N, 64)[:, 32:], pre.view(N, 64)[:, :32], cs.view(N, 32)], 1).contiguous()
+        pf = torch.zeros(N * corpus.PROOF_BYTES, dtype=torch.uint8, device="cuda"); prf = torch.zeros(N * 96, dtype=torch.uint8, device="cuda")
+        pst = torch.full((N,), 9, dtype=torch.uint8, device="cuda")
+        engine.batch_prove_spend_dev(N, tok.data_ptr(), ch.data_ptr(), None, seed, 0, pf.data_ptr(), prf.data_ptr(), pst.data_ptr(), S.cuda_stream)
+        ref = torch.zeros(N * 128, dtype=torch.uint8, device="cuda"); nul = torch.zeros(N * 32, dtype=torch.uint8, device="cuda")
+        vst = torch.full((N,), 9, dtype=torch.uint8, device="cuda")
+        engine.batch_verify_spend_and_refund_dev(N, pf.data_ptr(), rb(N * 128).data_ptr(), ref.data_ptr(), nul.data_ptr(), vst.data_ptr(), S.cuda_stream)
+        com = pf.view(N, corpus.PROOF_BYTES)[:, 128:128 + 4096].contiguous()
+        rst = torch.full((N,), 9, dtype=torch.uint8, device="cuda")
+        engine.batch_refund_check_dev(N, com.data_ptr(), ref.data_ptr(), rst.data_ptr(), S.cuda_stream)
+        S.synchronize()
+        assert (cst == 0).all() and (pst == 0).all() and (vst == 0).all() and (rst == 0).all()
+        assert (nul.view(N, 32) == pre.view(N, 64)[:, 32:]).all()                                    # nullifier() = the token's k
+        m = prf.view(N, 96)[:, 64:72].contiguous().view(torch.int64).view(N)
+        assert (m == credits - spend).all()                                                          # PreRefund.m = c - s
+    # a spot check of the device-generated proofs against the oracle verifier
+    o_ref, o_nul, o_st, _ = octx.batch_refund(pf[:4 * corpus.PROOF_BYTES].cpu().numpy(), np.zeros(4 * 128, np.uint8), threads=4)
+    assert (o_st == 0).all() and (o_nul == nul[:128].cpu().numpy()).all()
+    # overspend (s > c) is produced but rejected, as in the reference (src/tests.rs:366-374)
+    with torch.cuda.stream(S):
+        ch_bad = le32(credits + 1)
+        rb64 = rb(64 * 128)
+    engine.batch_prove_spend_dev(64, tok.data_ptr(), ch_bad.data_ptr(), None, seed, 0, pf.data_ptr(), prf.data_ptr(), pst.data_ptr(), S.cuda_stream)
+    engine.batch_verify_spend_and_refund_dev(64, pf.data_ptr(), rb64.data_ptr(), ref.data_ptr(), nul.data_ptr(), vst.data_ptr(), S.cuda_stream)
+    S.synchronize()
+    assert (vst[:64] == 7).all()

@@ -168,3 +168,26 @@ def test_cbor_skeletons_match_host_encoder_and_golden(act):
         assert HS.cbor_skeleton_unpack(kind, bytes(bad), act.RECORD_BYTES[kind])[1] == 0xFF
     assert HS.cbor_skeleton_encode(0, recs[0], 141).hex() == g["cbor_request"]
     assert HS.cbor_skeleton_encode(3, recs[3], 141).hex() == g["cbor_refund"]
+
+
+def test_client_generators_match_the_oracle_prover(octx):
+    """act_prove.cuh (PreIssuance::request, CreditToken::prove_spend) on the host build: bit-exact with the oracle's
+    line-by-line prover on identical RNG bytes, and the derived-stream mode equals the explicit mode on those bytes."""
+    n = 3
+    base = corpus.gen_valid(octx, n, seed=b"prover-parity", threads=2)
+    st = corpus.trip_streams(b"prover-parity", n)
+    hs = HS.Ctx(octx.h, octx.x, octx.w)
+    assert (hs.request(st["pre"], st["req_rnd"]) == base["req"]).all()
+    tokens, charges = corpus.tokens_from(base, st["pre"]), corpus.charges_from(base)
+    proofs, prer, status = hs.prove_spend(tokens, charges, rnd=st["prove_rnd"])
+    assert (status == 0).all() and (proofs == base["proofs"]).all() and (prer == base["prerefund"]).all()
+    seed = corpus.xof(b"derived-seed", 32)
+    rnd = np.frombuffer(b"".join(corpus.prover_stream(seed, 7 + i) for i in range(n)), np.uint8)
+    p1, r1, s1 = hs.prove_spend(tokens, charges, seed=seed, first_index=7)
+    p2, r2, s2 = hs.prove_spend(tokens, charges, rnd=rnd)
+    assert (p1 == p2).all() and (r1 == r2).all()
+    ref, nul, vst = hs.refund(p1, base["rnd"])
+    assert (vst == 0).all()
+    bad = tokens.copy(); bad[:32] = np.frombuffer(corpus.bad_point_encodings()[0], np.uint8)
+    p3, r3, s3 = hs.prove_spend(bad, charges, seed=seed)
+    assert s3.tolist() == [0x81, 0, 0] and not p3[:corpus.PROOF_BYTES].any() and (p3[corpus.PROOF_BYTES:] != 0).any()
