@@ -70,6 +70,7 @@ EXPORTED_SYMBOLS = [
     "act_encode_spend_proof_cbor", "act_encode_refund_cbor",
     "act_flag_replays", "act_flag_replays_dev", "act_unpack_cbor", "act_unpack_cbor_dev", "act_encode_cbor", "act_encode_cbor_dev",
     "act_batch_request", "act_batch_request_dev", "act_batch_prove_spend", "act_batch_prove_spend_dev",
+    "act_batch_issue_seq", "act_batch_verify_spend_and_refund_seq",
 ]
 
 
@@ -126,6 +127,8 @@ def load_library():
     lib.act_batch_request.argtypes = [vp, sz, vp, vp, vp]; lib.act_batch_request.restype = i32
     lib.act_batch_prove_spend_dev.argtypes = [vp, sz, vp, vp, vp, vp, u64, vp, vp, vp, vp]; lib.act_batch_prove_spend_dev.restype = i32
     lib.act_batch_prove_spend.argtypes = [vp, sz, vp, vp, vp, vp, u64, vp, vp, vp]; lib.act_batch_prove_spend.restype = i32
+    lib.act_batch_issue_seq.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, vp]; lib.act_batch_issue_seq.restype = i32
+    lib.act_batch_verify_spend_and_refund_seq.argtypes = [vp, sz, vp, vp, sz, vp, vp, vp, vp]; lib.act_batch_verify_spend_and_refund_seq.restype = i32
     _lib = lib
     return lib
 
@@ -278,6 +281,26 @@ class Engine:
         st = np.zeros(n, np.uint8)
         _check(self.lib.act_batch_refund_check(self._h, n, cm.ctypes.data, rf.ctypes.data, st.ctypes.data), "act_batch_refund_check")
         return st
+
+    # ---- sequential-RNG contract: same outputs as a loop of issue()/refund() calls sharing one RNG ----
+    def batch_issue_seq(self, requests, cs, rnd_stream):
+        """Request i uses rnd_stream[128*a_i : 128*a_i+128], a_i = accepted requests before i (the reference draws
+        randomness only after a request verifies).  Returns (responses, status, bytes consumed)."""
+        req = _u8(requests); n = req.size // REQUEST_BYTES
+        c = _u8(cs, n * 32, "cs"); r = _u8(rnd_stream)
+        resp = np.zeros(n * RESPONSE_BYTES, np.uint8); st = np.zeros(n, np.uint8); used = C.c_size_t(0)
+        _check(self.lib.act_batch_issue_seq(self._h, n, req.ctypes.data, c.ctypes.data, r.ctypes.data if r.size else None, r.size,
+                                            resp.ctypes.data, st.ctypes.data, C.addressof(used)), "act_batch_issue_seq")
+        return resp, st, int(used.value)
+
+    def batch_verify_spend_and_refund_seq(self, proofs, rnd_stream):
+        pf = _u8(proofs); n = pf.size // PROOF_BYTES
+        r = _u8(rnd_stream)
+        ref = np.zeros(n * REFUND_BYTES, np.uint8); nul = np.zeros(n * 32, np.uint8); st = np.zeros(n, np.uint8); used = C.c_size_t(0)
+        _check(self.lib.act_batch_verify_spend_and_refund_seq(self._h, n, pf.ctypes.data, r.ctypes.data if r.size else None, r.size,
+                                                              ref.ctypes.data, nul.ctypes.data, st.ctypes.data, C.addressof(used)),
+               "act_batch_verify_spend_and_refund_seq")
+        return ref, nul, st, int(used.value)
 
     # ---- client-side batch generators (fixture grade, not constant time) ----
     def batch_request(self, pre, rnd):

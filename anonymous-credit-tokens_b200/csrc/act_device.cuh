@@ -365,16 +365,27 @@ ACT_NOINLINE void bbs_sign_(const act_ctx* C, const ge* X_A, const u32* rnd, int
 // issue (src/lib.rs:621-663).  req: n x 32 words (K, gamma, k_bar, r_bar); cs: n x 8; rnd: n x 32;
 // resp: n x 40 words (A, e, gamma, z, c); status: n bytes.
 // =============================================================================================================
-ACT_FN void issue_thread(const act_ctx* C, size_t i, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status) {
+// mode ACT_MODE_FULL: verify, then sign with rnd[i] (the batch contract: request i owns 128 RNG bytes).
+// mode ACT_MODE_VERIFY: verify only (status[i]; nothing else is written).
+// mode ACT_MODE_SIGN: status[i] is given (by a VERIFY pass); accepted requests are signed with the RNG bytes at
+//      rnd + 32 * rnd_index[i] -- the position a sequential loop over ONE shared RNG would have reached (the reference
+//      draws e, alpha only after a request verifies, src/lib.rs:638-643).
+#define ACT_MODE_FULL 0
+#define ACT_MODE_VERIFY 1
+#define ACT_MODE_SIGN 2
+ACT_FN void issue_thread(const act_ctx* C, size_t i, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status,
+                         int mode = ACT_MODE_FULL, const u32* rnd_index = nullptr) {
     const u32* rq = req + 32 * i;
     u32* out = resp + 40 * i;
     u32 kw[8];
     load8(kw, rq);
     ge K;
     u32 valid = ristretto_decode_(&K, kw);
-    sc gamma = load_scalar(rq + 8), k_bar = load_scalar(rq + 16), r_bar = load_scalar(rq + 24);
     u32 st = ACT_ST_OK;
     if (!valid) st = ACT_ST_DECODE_INVALID_POINT;
+    if (mode == ACT_MODE_SIGN) st = status[i];
+    else {
+    sc gamma = load_scalar(rq + 8), k_bar = load_scalar(rq + 16), r_bar = load_scalar(rq + 24);
     // K1 = h2*k_bar + h3*r_bar - K*gamma                                                     (:629-630)
     vb_table tk;
     vb_table_build(&tk, K);
@@ -390,6 +401,8 @@ ACT_FN void issue_thread(const act_ctx* C, size_t i, const u32* req, const u32* 
         sc g2 = tr_challenge(&tr);
         if (st == ACT_ST_OK && !sc_eq(g2, gamma)) st = ACT_ST_INVALID_ISSUANCE_REQUEST_PROOF;   // (:638-640)
     }
+    }
+    if (mode == ACT_MODE_VERIFY) { status[i] = (u8)st; return; }
     if (st != ACT_ST_OK) {
         ACT_NOUNROLL for (int k = 0; k < 5; k++) store8_zero(out + 8 * k);
         status[i] = (u8)st;
@@ -402,7 +415,8 @@ ACT_FN void issue_thread(const act_ctx* C, size_t i, const u32* req, const u32* 
     u32 A_enc[8];
     sc e, g, z;
     u32 r[32];
-    ACT_NOUNROLL for (int k = 0; k < 4; k++) load8(r + 8 * k, rnd + 32 * i + 8 * k);
+    const u32* rsrc = rnd + 32 * (rnd_index ? (size_t)rnd_index[i] : i);
+    ACT_NOUNROLL for (int k = 0; k < 4; k++) load8(r + 8 * k, rsrc + 8 * k);
     bbs_sign_(C, &X_A, r, ACT_TR_RESPOND, &c, A_enc, &e, &g, &z);
     store8(out, A_enc); store_scalar(out + 8, e); store_scalar(out + 16, g); store_scalar(out + 24, z); store_scalar(out + 32, c);
     status[i] = ACT_ST_OK;
@@ -656,7 +670,7 @@ ACT_FN void spend_finish_thread(const act_ctx* C, size_t p, const u32* proofs, u
 // refunds: n x 32 words (A*, e*, gamma, z); nullifiers: n x 8 words (reduced k).
 // =============================================================================================================
 ACT_FN void refund_sign_thread(const act_ctx* C, size_t p, const u32* proofs, const u32* rnd, const u32* kprime,
-                               const u8* status, u32* refunds, u32* nullifiers) {
+                               const u8* status, u32* refunds, u32* nullifiers, const u32* rnd_index = nullptr, const u32* kwords = nullptr) {
     u32* out = refunds + 32 * p;
     if (status[p] != ACT_ST_OK) {
         ACT_NOUNROLL for (int k = 0; k < 4; k++) store8_zero(out + 8 * k);
@@ -668,12 +682,14 @@ ACT_FN void refund_sign_thread(const act_ctx* C, size_t p, const u32* proofs, co
     load_fe(&Kp.X, kp); load_fe(&Kp.Y, kp + 8); load_fe(&Kp.Z, kp + 16); load_fe(&Kp.T, kp + 24);
     ge X_A = ge_add(Kp, ge_basepoint());                                                   // (:848)
     u32 r[32];
-    ACT_NOUNROLL for (int k = 0; k < 4; k++) load8(r + 8 * k, rnd + 32 * p + 8 * k);
+    const u32* rsrc = rnd + 32 * (rnd_index ? (size_t)rnd_index[p] : p);   // sequential-RNG mode: see issue_thread
+    ACT_NOUNROLL for (int k = 0; k < 4; k++) load8(r + 8 * k, rsrc + 8 * k);
     u32 A_enc[8];
     sc e, g, z, dummy = sc_zero();
     bbs_sign_(C, &X_A, r, ACT_TR_REFUND, &dummy, A_enc, &e, &g, &z);
     store8(out, A_enc); store_scalar(out + 8, e); store_scalar(out + 16, g); store_scalar(out + 24, z);
-    store_scalar(nullifiers + 8 * p, load_scalar(proofs + (size_t)ACT_PROOF_WORDS * p));   // nullifier() = k (:720-722)
+    // nullifier() = k (:720-722); kwords: the k fields alone (n x 8 words) when the proofs are no longer resident
+    store_scalar(nullifiers + 8 * p, kwords ? load_scalar(kwords + 8 * p) : load_scalar(proofs + (size_t)ACT_PROOF_WORDS * p));
 }
 
 // =============================================================================================================

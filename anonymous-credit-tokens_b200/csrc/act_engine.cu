@@ -30,6 +30,17 @@ __global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issue_kernel(const act_ctx
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issue_thread(C, i, req, cs, rnd, resp, status);
 }
+// the two halves of issue for the sequential-RNG contract (act_batch_issue_seq)
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issue_mode_kernel(const act_ctx* C, size_t n, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status,
+                                                                       int mode, const u32* rnd_index) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) issue_thread(C, i, req, cs, rnd, resp, status, mode, rnd_index);
+}
+__global__ void __launch_bounds__(ACT_SIGN_BLOCK, 8) refund_sign_seq_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* rnd, const u32* kprime, const u8* status,
+                                                                           u32* refunds, u32* nullifiers, const u32* rnd_index, const u32* kwords) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) refund_sign_thread(C, p, proofs, rnd, kprime, status, refunds, nullifiers, rnd_index, kwords);
+}
 __global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issuance_check_kernel(const act_ctx* C, size_t n, const u32* K, const u32* resp, u8* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issuance_check_thread(C, i, K, resp, status);
@@ -555,16 +566,20 @@ extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* c
     return 0;
 }
 // one chunk of the spend pipeline on one stream with one scratch set
+// kprime_out != nullptr: verification only -- K' of every proof goes to kprime_out (m x 128 B) and the signing stage is left
+// to the caller (sequential-RNG contract)
 static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, size_t m, const u32* proofs, const u32* rnd,
-                              u32* refunds, u32* nullifiers, u8* status) {
+                              u32* refunds, u32* nullifiers, u8* status, u32* kprime_out = nullptr) {
     CK(cudaMemsetAsync(s->flags, 0, m * 4, st));
     unsigned rgrid = m < s->range_grid ? (unsigned)m : s->range_grid;
     LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<rgrid, ACT_L, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->flags, s->tabs, s->cpts)));
     LAUNCH(e, K_ENCODE, st, (spend_encode_kernel<<<nblocks(m * ACT_ENC_PARTS, ACT_ENC_BLOCK), ACT_ENC_BLOCK, 0, st>>>(e->d_ctx, m, s->cpts, s->items, 2 * ACT_L, 133)));
-    LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->kprime, s->flags)));
+    u32* kp = kprime_out ? kprime_out : s->kprime;
+    LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, kp, s->flags)));
     LAUNCH(e, K_CHUNK, st, (spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, s->items, s->cvs)));
     LAUNCH(e, K_FINISH, st, (spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status)));
-    LAUNCH(e, K_SIGN, st, (refund_sign_kernel<<<nblocks(m, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, m, proofs, rnd, s->kprime, status, refunds, nullifiers)));
+    if (!kprime_out)
+        LAUNCH(e, K_SIGN, st, (refund_sign_kernel<<<nblocks(m, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, m, proofs, rnd, s->kprime, status, refunds, nullifiers)));
     CK(cudaGetLastError());
     return 0;
 }
@@ -909,5 +924,113 @@ extern "C" int act_batch_prove_spend(act_engine* e, size_t n, const uint8_t* tok
 #undef CKB
     } while (0);
     cudaFree(d_tk); cudaFree(d_ch); cudaFree(d_rnd); cudaFree(d_pf); cudaFree(d_pr); cudaFree(d_st);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sequential-RNG contract: outputs identical to a loop of issue() / refund() calls over ONE shared RNG.
+// The reference draws e and alpha only after a request verifies (src/lib.rs:638-643, 842-846), so request i uses the
+// 128 bytes at offset 128 * (number of accepted requests before i) of the caller's stream.  Pass 1 verifies the whole
+// batch, the host turns the accept bits into stream positions, pass 2 signs.
+// ---------------------------------------------------------------------------------------------------
+static int seq_positions(const std::vector<u8>& st, std::vector<u32>& idx, size_t stream_len, size_t* consumed) {
+    size_t acc = 0;
+    idx.resize(st.size());
+    for (size_t i = 0; i < st.size(); i++) { idx[i] = (u32)acc; if (st[i] == 0) acc++; }
+    if (consumed) *consumed = acc * 128;
+    if (acc * 128 > stream_len) return fail_msg("sequential-RNG call: the RNG stream is shorter than 128 bytes per accepted request");
+    return 0;
+}
+extern "C" int act_batch_issue_seq(act_engine* e, size_t n, const uint8_t* req, const uint8_t* c, const uint8_t* rnd_stream, size_t rnd_stream_len,
+                                   uint8_t* resp, uint8_t* status, size_t* consumed) {
+    if (!e) return fail_msg("null engine");
+    if (consumed) *consumed = 0;
+    if (n == 0) return 0;
+    if (!req || !c || !resp || !status || (!rnd_stream && rnd_stream_len)) return fail_msg("act_batch_issue_seq: null buffer");
+    if (n >= 0xffffffffu) return fail_msg("act_batch_issue_seq: batch too large");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream[0];
+    u8 *d_req = nullptr, *d_c = nullptr, *d_rnd = nullptr, *d_resp = nullptr, *d_st = nullptr; u32* d_idx = nullptr;
+    int rc = 0;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaMalloc((void**)&d_req, n * 128)); CKB(cudaMalloc((void**)&d_c, n * 32)); CKB(cudaMalloc((void**)&d_resp, n * 160));
+        CKB(cudaMalloc((void**)&d_st, n)); CKB(cudaMalloc((void**)&d_idx, n * 4));
+        CKB(cudaMemcpyAsync(d_req, req, n * 128, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(d_c, c, n * 32, cudaMemcpyHostToDevice, st));
+        issue_mode_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)d_req, (const u32*)d_c, nullptr, (u32*)d_resp, d_st, ACT_MODE_VERIFY, nullptr);
+        std::vector<u8> hst(n);
+        CKB(cudaMemcpyAsync(hst.data(), d_st, n, cudaMemcpyDeviceToHost, st));
+        CKB(cudaStreamSynchronize(st));
+        std::vector<u32> idx;
+        size_t used = 0;
+        if ((rc = seq_positions(hst, idx, rnd_stream_len, &used))) break;
+        if (consumed) *consumed = used;
+        CKB(cudaMalloc((void**)&d_rnd, used ? used : 128));
+        if (used) CKB(cudaMemcpyAsync(d_rnd, rnd_stream, used, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
+        issue_mode_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)d_req, (const u32*)d_c, (const u32*)d_rnd, (u32*)d_resp, d_st, ACT_MODE_SIGN, d_idx);
+        e->launches += 2;
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpyAsync(resp, d_resp, n * 160, cudaMemcpyDeviceToHost, st));
+        CKB(cudaMemcpyAsync(status, d_st, n, cudaMemcpyDeviceToHost, st));
+        CKB(cudaStreamSynchronize(st));
+#undef CKB
+    } while (0);
+    cudaFree(d_req); cudaFree(d_c); cudaFree(d_rnd); cudaFree(d_resp); cudaFree(d_st); cudaFree(d_idx);
+    return rc;
+}
+extern "C" int act_batch_verify_spend_and_refund_seq(act_engine* e, size_t n, const uint8_t* proofs, const uint8_t* rnd_stream, size_t rnd_stream_len,
+                                                      uint8_t* refunds, uint8_t* nullifiers, uint8_t* status, size_t* consumed) {
+    if (!e) return fail_msg("null engine");
+    if (consumed) *consumed = 0;
+    if (n == 0) return 0;
+    if (!proofs || !refunds || !nullifiers || !status || (!rnd_stream && rnd_stream_len)) return fail_msg("act_batch_verify_spend_and_refund_seq: null buffer");
+    if (n >= 0xffffffffu) return fail_msg("act_batch_verify_spend_and_refund_seq: batch too large");
+    CK(cudaSetDevice(e->device));
+    u8 *d_st = nullptr, *d_rnd = nullptr, *d_ref = nullptr, *d_nul = nullptr; u32 *d_kp = nullptr, *d_idx = nullptr, *d_k = nullptr;
+    u8* d_pf[2] = {nullptr, nullptr};
+    int rc = 0;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        size_t cap = n < ACT_SPEND_CHUNK ? n : ACT_SPEND_CHUNK;
+        if ((rc = ensure_scratch(&e->scratch[0], cap)) || (rc = ensure_scratch(&e->scratch[1], cap))) break;
+        CKB(cudaMalloc((void**)&d_st, n)); CKB(cudaMalloc((void**)&d_kp, n * 128)); CKB(cudaMalloc((void**)&d_idx, n * 4));
+        CKB(cudaMalloc((void**)&d_ref, n * 128)); CKB(cudaMalloc((void**)&d_nul, n * 32)); CKB(cudaMalloc((void**)&d_k, n * 32));
+        CKB(cudaMalloc((void**)&d_pf[0], cap * ACT_PROOF_BYTES)); CKB(cudaMalloc((void**)&d_pf[1], cap * ACT_PROOF_BYTES));
+        // pass 1: verification, chunks alternating over the two streams; K' of every proof is kept
+        size_t ci = 0;
+        for (size_t off = 0; off < n && !rc; off += ACT_SPEND_CHUNK, ci++) {
+            size_t m = n - off < ACT_SPEND_CHUNK ? n - off : ACT_SPEND_CHUNK;
+            int s = (int)(ci & 1);
+            CKB(cudaStreamSynchronize(e->stream[s]));
+            CKB(cudaMemcpyAsync(d_pf[s], proofs + off * ACT_PROOF_BYTES, m * ACT_PROOF_BYTES, cudaMemcpyHostToDevice, e->stream[s]));
+            rc = spend_chunk_launch(e, &e->scratch[s], e->stream[s], m, (const u32*)d_pf[s], nullptr, nullptr, nullptr, d_st + off, d_kp + off * 32);
+            // item 0 of the transcript is the reduced k: keep it for the nullifier output of pass 2
+            CKB(cudaMemcpy2DAsync(d_k + off * 8, 32, e->scratch[s].items, (size_t)ACT_ITEM_WORDS * 4, 32, m, cudaMemcpyDeviceToDevice, e->stream[s]));
+        }
+        if (rc) break;
+        CKB(cudaStreamSynchronize(e->stream[0])); CKB(cudaStreamSynchronize(e->stream[1]));
+        std::vector<u8> hst(n);
+        CKB(cudaMemcpy(hst.data(), d_st, n, cudaMemcpyDeviceToHost));
+        std::vector<u32> idx;
+        size_t used = 0;
+        if ((rc = seq_positions(hst, idx, rnd_stream_len, &used))) break;
+        if (consumed) *consumed = used;
+        CKB(cudaMalloc((void**)&d_rnd, used ? used : 128));
+        cudaStream_t st = e->stream[0];
+        if (used) CKB(cudaMemcpyAsync(d_rnd, rnd_stream, used, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
+        // pass 2: one launch signs every accepted proof with its position in the stream
+        refund_sign_seq_kernel<<<nblocks(n, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, n, nullptr, (const u32*)d_rnd, d_kp, d_st, (u32*)d_ref, (u32*)d_nul, d_idx, d_k);
+        e->launches += 1;
+        CKB(cudaStreamSynchronize(st));
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpy(refunds, d_ref, n * 128, cudaMemcpyDeviceToHost));
+        CKB(cudaMemcpy(nullifiers, d_nul, n * 32, cudaMemcpyDeviceToHost));
+        memcpy(status, hst.data(), n);
+#undef CKB
+    } while (0);
+    cudaFree(d_st); cudaFree(d_kp); cudaFree(d_idx); cudaFree(d_k); cudaFree(d_ref); cudaFree(d_nul); cudaFree(d_rnd); cudaFree(d_pf[0]); cudaFree(d_pf[1]);
     return rc;
 }

@@ -45,7 +45,7 @@ LIMB_MACS_PER_ISSUE = 6.7e5
 # 0.5 instructions/clock/SMSP; profiles/r01d_*.txt) -> integer-multiply roofline = SMs x 32 x SM clock
 IMAD_WIDE_LANES_PER_CLK_PER_SM = 32
 PROOF_BYTES = 16832
-UNIQUE_PROOFS = 2048                 # unique valid proofs synthesised on the CPU, tiled to the batch size
+UNIQUE_PROOFS = 2048                 # valid proofs from the ORACLE prover: CPU baseline sample + cross-check of the engine
 UNIQUE_REQUESTS = 16384
 
 
@@ -199,31 +199,57 @@ def main():
     peak_microbench = act.measure_int_mul_peak(local)
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
 
-    def tile_to(dst_t, src_np, rec, count, shift):
-        """fill device tensor with `count` records by tiling the unique set (rotated by `shift` records)."""
-        u = len(src_np) // rec
-        src = torch.from_numpy(np.roll(src_np.reshape(u, rec), -shift, axis=0).copy()).to(dev)
-        v = dst_t.view(-1, rec)
-        for off in range(0, count, u):
-            m = min(u, count - off)
-            v[off:off + m] = src[:m]
+    # a real (non-default) stream: torch ops, the engine's launches and the timing events all go to it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
+    # ---- device-side fixture generation (untimed): n UNIQUE tokens are requested, issued and spent on this GPU by the engine's
+    # client-side generators (act_batch_request -> act_batch_issue -> act_batch_prove_spend; bit-exact with the oracle prover,
+    # tests/test_gpu_parity.py), so no proof in the batch repeats.  Seeds are fixed per rank.
+    gen = torch.Generator(device=dev); gen.manual_seed(20261017 + rank)
+
+    def rbytes(k):
+        return torch.randint(0, 256, (k,), dtype=torch.uint8, device=dev, generator=gen)
+
+    def le32(v, count):
+        sh = 8 * torch.arange(2, device=dev)
+        return torch.cat([((v.view(count, 1) >> sh) & 0xff).to(torch.uint8), torch.zeros(count, 30, dtype=torch.uint8, device=dev)], 1).reshape(-1)
+
+    def make_requests(count):
+        pre = rbytes(count * 64); pv = pre.view(count, 64); pv[:, 31] &= 0x0f; pv[:, 63] &= 0x0f   # PreIssuance r, k (< 2^252)
+        req = torch.empty(count * 128, dtype=torch.uint8, device=dev)
+        eng.batch_request_dev(count, pre.data_ptr(), rbytes(count * 128).data_ptr(), req.data_ptr(), stream)
+        credits = torch.randint(20, 1000, (count,), device=dev, generator=gen)                     # benches/benchmark.rs:60,178
+        torch.cuda.synchronize()
+        return pre, req, credits
+
+    t_gen = time.time()
+    pre, d_req_s, credits = make_requests(n)
+    d_cs_s = le32(credits, n)
+    d_resp_s = torch.empty(n * 160, dtype=torch.uint8, device=dev); d_ist_s = torch.empty(n, dtype=torch.uint8, device=dev)
+    eng.batch_issue_dev(n, d_req_s.data_ptr(), d_cs_s.data_ptr(), rbytes(n * 128).data_ptr(), d_resp_s.data_ptr(), d_ist_s.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert bool((d_ist_s == 0).all()), "fixture issuance rejected a request"
+    tokens = torch.cat([d_resp_s.view(n, 160)[:, :64], pre.view(n, 64)[:, 32:], pre.view(n, 64)[:, :32], d_cs_s.view(n, 32)], 1).contiguous()
+    spend = (torch.rand(n, device=dev, generator=gen) * (credits - 1)).long() + 1                  # charge in [1, c-1] (benchmark.rs:194-201)
+    d_charges = le32(spend, n)
     d_proofs = torch.empty(n * PROOF_BYTES, dtype=torch.uint8, device=dev)
-    d_rnd = torch.empty(n * 128, dtype=torch.uint8, device=dev)
-    tile_to(d_proofs, base["proofs"], PROOF_BYTES, n, rank * 7)
-    tile_to(d_rnd, base["rnd"], 128, n, rank * 7)
+    d_prer = torch.empty(n * 96, dtype=torch.uint8, device=dev); d_pst = torch.empty(n, dtype=torch.uint8, device=dev)
+    prove_seed = bytes([(7 * i + rank) & 0xff for i in range(32)])
+    eng.batch_prove_spend_dev(n, tokens.data_ptr(), d_charges.data_ptr(), None, prove_seed, rank * n, d_proofs.data_ptr(), d_prer.data_ptr(), d_pst.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert bool((d_pst == 0).all())
+    d_rnd = rbytes(n * 128)
+    del d_resp_s, d_ist_s, d_prer, d_pst, tokens, pre, d_req_s, d_cs_s
+    log(f"[bench] rank {rank}: {n} unique tokens issued and spent on the device in {time.time() - t_gen:.1f}s")
     d_ref = torch.zeros(n * 128, dtype=torch.uint8, device=dev)
     d_nul = torch.zeros(n * 32, dtype=torch.uint8, device=dev)
     d_st = torch.zeros(n, dtype=torch.uint8, device=dev)
     if world > 1:
         g_st = torch.empty(world * n, dtype=torch.uint8, device=dev)
         g_nul = torch.empty(world * n * 32, dtype=torch.uint8, device=dev)
-    # a real (non-default) stream: the engine launches on it and torch's events are recorded on it
-    tstream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
-
     def spend_step():
         eng.batch_verify_spend_and_refund_dev(n, d_proofs.data_ptr(), d_rnd.data_ptr(), d_ref.data_ptr(), d_nul.data_ptr(), d_st.data_ptr(), stream)
         if world > 1:   # the one collective on the path: gather accept bits and nullifiers (33 B / proof)
@@ -280,11 +306,14 @@ def main():
     # parity guard inside the bench: every proof of the valid batch accepted, refunds equal the oracle's for a sample
     st_host = d_st.cpu().numpy()
     assert (st_host == 0).all(), f"bench batch not fully accepted: {np.unique(st_host, return_counts=True)}"
-    chk = 4
-    o_ref, o_nul, o_st, _ = ctx.batch_refund(np.roll(base["proofs"].reshape(-1, PROOF_BYTES), -rank * 7, axis=0)[:chk].reshape(-1).copy(),
-                                             np.roll(base["rnd"].reshape(-1, 128), -rank * 7, axis=0)[:chk].reshape(-1).copy(), threads=chk)
+    chk = 4   # the oracle verifies and refunds a sample of the device-generated proofs: identical bytes
+    o_ref, o_nul, o_st, _ = ctx.batch_refund(d_proofs[:chk * PROOF_BYTES].cpu().numpy(), d_rnd[:chk * 128].cpu().numpy(), threads=chk)
+    assert (o_st == 0).all(), "oracle rejects a device-generated proof"
     assert (d_ref[:chk * 128].cpu().numpy() == o_ref).all() and (d_nul[:chk * 32].cpu().numpy() == o_nul).all(), "bench output differs from oracle"
-
+    # ... and the engine verifies a sample of the ORACLE prover's proofs (CPU fixtures) to the oracle's bytes
+    o2_ref, o2_nul, o2_st, _ = ctx.batch_refund(base["proofs"][:chk * PROOF_BYTES], base["rnd"][:chk * 128], threads=chk)
+    g2 = eng.batch_verify_spend_and_refund(base["proofs"][:chk * PROOF_BYTES], base["rnd"][:chk * 128])
+    assert (g2[2] == o2_st).all() and (g2[0] == o2_ref).all() and (g2[1] == o2_nul).all()
     rng_ms, rng_cnt = ktimes["spend_range"]
     per_launch_proofs = n * Kr / max(rng_cnt, 1)
     achieved = LIMB_MACS_PER_SPEND_RANGE * per_launch_proofs / (rng_ms / max(rng_cnt, 1) * 1e-3) if rng_ms else None
@@ -321,9 +350,10 @@ def main():
     }
 
     # ---- issue (configs[1]) device-resident ----
-    d_req = torch.empty(ni * 128, dtype=torch.uint8, device=dev); d_cs = torch.empty(ni * 32, dtype=torch.uint8, device=dev)
-    d_irnd = torch.empty(ni * 128, dtype=torch.uint8, device=dev)
-    tile_to(d_req, reqs["req"], 128, ni, rank * 7); tile_to(d_cs, reqs["cs"], 32, ni, rank * 7); tile_to(d_irnd, reqs["rnd"], 128, ni, rank * 7)
+    _pre, d_req, icred = make_requests(ni)
+    d_cs = le32(icred, ni)
+    d_irnd = rbytes(ni * 128)
+    del _pre
     d_resp = torch.zeros(ni * 160, dtype=torch.uint8, device=dev); d_ist = torch.zeros(ni, dtype=torch.uint8, device=dev)
 
     def issue_step():
@@ -331,21 +361,17 @@ def main():
 
     ims = timed(issue_step, W, K)
     assert (d_ist.cpu().numpy() == 0).all()
-    o_resp, o_ist, _ = ctx.batch_issue(np.roll(reqs["req"].reshape(-1, 128), -rank * 7, axis=0)[:8].reshape(-1).copy(),
-                                       np.roll(reqs["cs"].reshape(-1, 32), -rank * 7, axis=0)[:8].reshape(-1).copy(),
-                                       np.roll(reqs["rnd"].reshape(-1, 128), -rank * 7, axis=0)[:8].reshape(-1).copy(), threads=8)
-    assert (d_resp[:8 * 160].cpu().numpy() == o_resp).all(), "issue output differs from oracle"
+    o_resp, o_ist, _ = ctx.batch_issue(d_req[:8 * 128].cpu().numpy(), d_cs[:8 * 32].cpu().numpy(), d_irnd[:8 * 128].cpu().numpy(), threads=8)
+    assert (o_ist == 0).all() and (d_resp[:8 * 160].cpu().numpy() == o_resp).all(), "issue output differs from oracle"
     issue_value = world * ni * K / (ims * 1e-3)
 
     # ---- e2e: pinned host buffers through the public C ABI (H2D + kernels + D2H inside the timed region) ----
     Ke = args.e2e_steps or K
+    h_proofs = torch.empty(n * PROOF_BYTES, dtype=torch.uint8, pin_memory=True)
+    h_proofs.copy_(d_proofs)
+    hq = torch.empty(ni * 128, dtype=torch.uint8, pin_memory=True); hq.copy_(d_req)
     del d_proofs, d_req
     torch.cuda.empty_cache()
-    h_proofs = torch.empty(n * PROOF_BYTES, dtype=torch.uint8, pin_memory=True)
-    u = UNIQUE_PROOFS
-    hv = h_proofs.view(-1, PROOF_BYTES); src = torch.from_numpy(base["proofs"].reshape(u, PROOF_BYTES))
-    for off in range(0, n, u):
-        m = min(u, n - off); hv[off:off + m] = src[:m]
     h_rnd = d_rnd.cpu().pin_memory()
     h_ref = torch.empty(n * 128, dtype=torch.uint8, pin_memory=True); h_nul = torch.empty(n * 32, dtype=torch.uint8, pin_memory=True)
     h_st = torch.empty(n, dtype=torch.uint8, pin_memory=True)
@@ -365,7 +391,6 @@ def main():
     assert (h_st.numpy() == 0).all()
     e2e_value = world * n * Ke / e2e_s
 
-    hq = torch.from_numpy(np.tile(reqs["req"].reshape(-1, 128), ((ni + UNIQUE_REQUESTS - 1) // UNIQUE_REQUESTS, 1))[:ni].reshape(-1).copy()).pin_memory()
     hc = d_cs.cpu().pin_memory(); hr = d_irnd.cpu().pin_memory()
     hresp = torch.empty(ni * 160, dtype=torch.uint8, pin_memory=True); hst = torch.empty(ni, dtype=torch.uint8, pin_memory=True)
 
@@ -389,7 +414,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer)",
             "data": "synthetic",
             "config": {"workload": f"batch_verify_spend_and_refund of {n} SpendProofs per GPU (BASELINE configs[2]; x{world} GPUs = configs[3] shape), L=128, bench params",
-                       "unique_proofs": UNIQUE_PROOFS, "tiling": "valid proofs from the oracle prover tiled to the batch size",
+                       "fixtures": f"{n} unique tokens per GPU requested, issued and spent on the device by the engine's generators (bit-exact with the oracle prover); charges uniform in [1, c-1], c in [20, 1000)",
                        "l2": "inputs (17.6 GB per step) far larger than L2; no flush needed",
                        "collective": "all_gather of status+nullifiers (33 B/proof) inside the step" if world > 1 else "none (single GPU)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (PROOF_BYTES + 128), "d2h_bytes_per_step": n * 161, "steps": Ke,

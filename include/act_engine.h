@@ -165,6 +165,16 @@ ACT_API int act_encode_cbor_dev(act_engine* e, int kind, size_t n, const void* r
 ACT_API int act_unpack_cbor(act_engine* e, int kind, size_t n, const uint8_t* cbor, uint8_t* records, uint8_t* status);
 ACT_API int act_encode_cbor(act_engine* e, int kind, size_t n, const uint8_t* records, uint8_t* cbor);
 
+/* Sequential-RNG contract: outputs identical to a loop of PrivateKey::issue / PrivateKey::refund calls over ONE shared RNG.
+ * The reference draws e and alpha (64 bytes each) only after a request verifies (src/lib.rs:638-643, 842-846), so
+ * request i uses the 128 bytes at offset 128 * (number of accepted requests before i) of rnd_stream.  *consumed
+ * (optional) receives the number of stream bytes used; the call fails if the stream is shorter than that.
+ * Host buffers; two passes (verify, then sign) with one host-side scan of the accept bits in between. */
+ACT_API int act_batch_issue_seq(act_engine* e, size_t n, const uint8_t* req, const uint8_t* c, const uint8_t* rnd_stream, size_t rnd_stream_len,
+                                uint8_t* resp, uint8_t* status, size_t* consumed);
+ACT_API int act_batch_verify_spend_and_refund_seq(act_engine* e, size_t n, const uint8_t* proofs, const uint8_t* rnd_stream, size_t rnd_stream_len,
+                                                   uint8_t* refunds, uint8_t* nullifiers, uint8_t* status, size_t* consumed);
+
 /* Client-side batch generators, bit-exact with the reference's prover for the same RNG bytes but NOT
  * constant time: they exist to synthesise full-size batches of valid, unique fixtures on the device.
  *   act_batch_request      = n x PreIssuance::request          src/lib.rs:463-487

@@ -331,3 +331,48 @@ def test_client_generators_on_gpu(act, engine, octx):
     engine.batch_verify_spend_and_refund_dev(64, pf.data_ptr(), rb64.data_ptr(), ref.data_ptr(), nul.data_ptr(), vst.data_ptr(), S.cuda_stream)
     S.synchronize()
     assert (vst[:64] == 7).all()
+
+
+def test_sequential_rng_contract(engine, octx, base):
+    """act_batch_*_seq == a loop of reference calls over ONE shared RNG: randomness is consumed only by accepted
+    requests, in slice order (src/lib.rs:638-643, 842-846)."""
+    proofs, rnd, expect, labels = corpus.mutate_proofs(octx, base)
+    n = len(expect)
+    stream = np.frombuffer(corpus.xof(b"one-shared-rng", 128 * n), np.uint8)
+    ref, nul, st, used = engine.batch_verify_spend_and_refund_seq(proofs, stream)
+    pos = 0
+    for i in range(n):
+        o_st, o_ref, o_nul = octx.refund(proofs[i * corpus.PROOF_BYTES:(i + 1) * corpus.PROOF_BYTES].tobytes(), stream[pos:pos + 128].tobytes())
+        assert st[i] == o_st, (i, labels[i])
+        if o_st == 0:
+            pos += 128
+            assert ref[128 * i:128 * i + 128].tobytes() == o_ref and nul[32 * i:32 * i + 32].tobytes() == o_nul, (i, labels[i])
+        else:
+            assert not ref[128 * i:128 * i + 128].any() and not nul[32 * i:32 * i + 32].any()
+    assert used == pos and 0 < pos < 128 * n
+    with pytest.raises(Exception):
+        engine.batch_verify_spend_and_refund_seq(proofs, stream[:pos - 1])       # stream too short
+    req, cs, irnd, iexp, ilab = corpus.mutate_requests(octx, base)
+    resp, ist, iused = engine.batch_issue_seq(req, cs, stream)
+    pos = 0
+    for i in range(len(iexp)):
+        o_st, o_resp = octx.issue(req[128 * i:128 * i + 128].tobytes(), cs[32 * i:32 * i + 32].tobytes(), stream[pos:pos + 128].tobytes())
+        assert ist[i] == o_st, (i, ilab[i])
+        if o_st == 0:
+            pos += 128
+            assert resp[160 * i:160 * i + 160].tobytes() == o_resp
+        else:
+            assert not resp[160 * i:160 * i + 160].any()
+    assert iused == pos
+    # a batch that crosses the pipeline chunk (two streams) still lines up with the stream positions
+    u = n; N = 20000
+    idx = (np.arange(N) * 11 + 5) % u
+    P = proofs.reshape(u, -1)[idx].reshape(-1).copy()
+    big = np.frombuffer(corpus.xof(b"one-shared-rng-big", 128 * N), np.uint8)
+    r2, n2, s2, used2 = engine.batch_verify_spend_and_refund_seq(P, big)
+    acc = np.flatnonzero(s2 == 0)
+    assert used2 == 128 * len(acc) and (s2 == st[idx]).all()
+    packed = big[:used2].reshape(-1, 128)
+    full_rnd = np.zeros((N, 128), np.uint8); full_rnd[acc] = packed
+    r3, n3, s3 = engine.batch_verify_spend_and_refund(P, full_rnd.reshape(-1))
+    assert (r3 == r2).all() and (n3 == n2).all() and (s3 == s2).all()
