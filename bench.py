@@ -367,7 +367,13 @@ def main():
 
     # ---- e2e: pinned host buffers through the public C ABI (H2D + kernels + D2H inside the timed region) ----
     Ke = args.e2e_steps or K
-    h_proofs = torch.empty(n * PROOF_BYTES, dtype=torch.uint8, pin_memory=True)
+    host_mem = "pinned"
+    try:
+        h_proofs = torch.empty(n * PROOF_BYTES, dtype=torch.uint8, pin_memory=True)
+    except RuntimeError as ex:   # a box that cannot page-lock world x 17.6 GB: the same bytes from pageable memory (slower copies)
+        log(f"[bench] rank {rank}: pinned allocation failed ({ex}); using pageable host memory for the e2e leg")
+        h_proofs = torch.empty(n * PROOF_BYTES, dtype=torch.uint8)
+        host_mem = "pageable (pinned allocation failed)"
     h_proofs.copy_(d_proofs)
     hq = torch.empty(ni * 128, dtype=torch.uint8, pin_memory=True); hq.copy_(d_req)
     del d_proofs, d_req
@@ -418,7 +424,7 @@ def main():
                        "l2": "inputs (17.6 GB per step) far larger than L2; no flush needed",
                        "collective": "all_gather of status+nullifiers (33 B/proof) inside the step" if world > 1 else "none (single GPU)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (PROOF_BYTES + 128), "d2h_bytes_per_step": n * 161, "steps": Ke,
-                    "api": "act_batch_verify_spend_and_refund (C ABI, pinned host buffers)"},
+                    "api": f"act_batch_verify_spend_and_refund (C ABI, {host_mem} host buffers)"},
             "issue": {"metric": "issues_per_sec", "value": issue_value, "unit": "issues/s", "ms_per_step": ims / K, "n": ni,
                       "workload": f"batch_issue of {ni} IssuanceRequests per GPU (BASELINE configs[1])",
                       "e2e": {"value": world * ni * Ke / e2e_issue_s, "h2d_bytes_per_step": ni * 288, "d2h_bytes_per_step": ni * 161},
