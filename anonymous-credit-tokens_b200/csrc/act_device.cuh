@@ -37,19 +37,33 @@
 #define ACT_SPEND_BYTES 15784u      // 184 + 40*390
 #define ACT_SPEND_CHUNKS 16
 
-// fixed-base tables (public scalars): signed radix 2^ACT_FB_BITS, entry |d| in 0..2^(BITS-1) (0 = identity), affine
-// Niels.  BITS = 13: 20 windows x 4097 entries x 96 B = 7.9 MB per base (L2 resident), 20 mixed additions per
-// scalar multiplication instead of 32 with radix 256.
+// fixed-base tables (public scalars): signed radix 2^bits, entry |d| in 0..2^(bits-1) (0 = identity), affine Niels,
+// ceil(254/bits) windows -> that many mixed additions per scalar multiplication and no doublings.  The width is a
+// property of each table (fb_tab): the two bases every range-proof commitment touches (H1, H3) get 2^16 windows
+// (16 additions, 50 MB per base), G and H2 get 2^13 (20 additions, 7.9 MB per base); all L2/HBM resident.
 #ifndef ACT_FB_BITS
-#define ACT_FB_BITS 13
+#define ACT_FB_BITS 13          // G, H2
 #endif
-#define ACT_FB_WIN ((253 + ACT_FB_BITS) / ACT_FB_BITS)
-#define ACT_FB_ENT ((1 << (ACT_FB_BITS - 1)) + 1)
-#define ACT_FB_SIZE (ACT_FB_WIN * ACT_FB_ENT)
-// table construction is split over ACT_FB_PARTS threads per window (each converts its entries to affine with
-// batched inversions of ACT_FB_BATCH points)
-#define ACT_FB_PARTS (ACT_FB_BITS > 9 ? 8 : 1)
+#ifndef ACT_FB_BITS_HOT
+#define ACT_FB_BITS_HOT 16      // H1, H3
+#endif
+// table construction: one thread per (window, part of ACT_FB_PART entries), entries converted to affine with batched
+// inversions of ACT_FB_BATCH points
+#define ACT_FB_PART 512
 #define ACT_FB_BATCH 16
+#if defined(__CUDACC__)
+#define ACT_HD __host__ __device__ __forceinline__
+#else
+#define ACT_HD static inline
+#endif
+struct fb_tab {
+    const ge_niels* p;
+    u32 bits, win, ent;     // window width, number of windows, entries per window (2^(bits-1) + 1)
+};
+ACT_HD u32 fb_win_of(u32 bits) { return (253u + bits) / bits; }
+ACT_HD u32 fb_ent_of(u32 bits) { return (1u << (bits - 1)) + 1u; }
+ACT_HD size_t fb_size_of(u32 bits) { return (size_t)fb_win_of(bits) * fb_ent_of(bits); }
+ACT_HD u32 fb_parts_of(u32 bits) { u32 n = fb_ent_of(bits) - 1; return n >= ACT_FB_PART ? n / ACT_FB_PART : 1; }
 // constant-time basepoint table: signed radix-16, 64 windows, |d| in 0..8
 #define ACT_CT_WIN 64
 #define ACT_CT_ENT 9
@@ -66,7 +80,7 @@
 #define ACT_BASE_H3 3
 
 struct act_ctx {
-    const ge_niels* fb[4];   // vartime fixed-base tables for G, H1, H2, H3 (global memory, L2 resident)
+    fb_tab fb[4];            // vartime fixed-base tables for G, H1, H2, H3 (global memory, L2 resident)
     const ge_niels* ct_g;    // constant-time table for G
     sc x;                    // issuer secret
     ge W;                    // issuer public key
@@ -144,10 +158,9 @@ ACT_FN void prefetch_line(const void* p) {
 }
 
 // ---- fixed-base accumulation (public scalars) ---------------------------------------------------------
-// signed radix-2^ACT_FB_BITS digit i of a scalar s < 2^253: raw window plus the carry of the window below, mapped to
-// (-2^(BITS-1), 2^(BITS-1)].  Public scalars only (the carry is data dependent).
-ACT_FN int fb_digit(const sc& s, int i, u32* carry) {
-    const u32 W = ACT_FB_BITS;
+// signed radix-2^W digit i of a scalar s < 2^253: raw window plus the carry of the window below, mapped to
+// (-2^(W-1), 2^(W-1)].  Public scalars only (the carry is data dependent).
+ACT_FN int fb_digit(const sc& s, u32 W, int i, u32* carry) {
     u32 bit = W * (u32)i, w = bit >> 5, sh = bit & 31u;
     u32 lo = s.v[w], hi = (w + 1 < 8) ? s.v[w + 1] : 0u;
     u32 raw = (sh ? ((lo >> sh) | (hi << (32u - sh))) : lo) & ((1u << W) - 1u);
@@ -155,18 +168,18 @@ ACT_FN int fb_digit(const sc& s, int i, u32* carry) {
     *carry = (d > (1 << (W - 1))) ? 1u : 0u;
     return d - (int)(*carry << W);
 }
-// acc += (negate ? -s : s) * B using the wide-window table of B: ACT_FB_WIN mixed additions, no doublings.
-ACT_FN ge fb_accumulate(ge acc, const ge_niels* tab, const sc& s, bool negate) {
+// acc += (negate ? -s : s) * B using the wide-window table of B: T.win mixed additions, no doublings.
+ACT_FN ge fb_accumulate(ge acc, const fb_tab& T, const sc& s, bool negate) {
     u32 carry = 0;
-    int d = fb_digit(s, 0, &carry);
-    ACT_NOUNROLL for (int i = 0; i < ACT_FB_WIN; i++) {
+    int d = fb_digit(s, T.bits, 0, &carry);
+    ACT_NOUNROLL for (u32 i = 0; i < T.win; i++) {
         u32 neg = (d < 0) ? 1u : 0u;
         u32 idx = (u32)(d < 0 ? -d : d);
         if (negate) neg ^= 1u;
-        const ge_niels* cur = tab + i * ACT_FB_ENT + idx;
-        if (i + 1 < ACT_FB_WIN) {   // next window's entry (96 B: may straddle two lines) travels while this addition runs
-            d = fb_digit(s, i + 1, &carry);
-            const ge_niels* nxt = tab + (i + 1) * ACT_FB_ENT + (u32)(d < 0 ? -d : d);
+        const ge_niels* cur = T.p + (size_t)i * T.ent + idx;
+        if (i + 1 < T.win) {   // next window's entry (96 B: may straddle two lines) travels while this addition runs
+            d = fb_digit(s, T.bits, (int)i + 1, &carry);
+            const ge_niels* nxt = T.p + (size_t)(i + 1) * T.ent + (u32)(d < 0 ? -d : d);
             prefetch_line(nxt); prefetch_line(reinterpret_cast<const u8*>(nxt) + 95);
         }
         ge_niels e = load_niels(cur);
@@ -499,12 +512,12 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
         gb = sc_half(gb);
         ge Q = vb_mul_split_neg<ACT_RANGE_SPLIT>(tabs, gb);
         ACT_NOUNROLL for (int t = 0; t < 3; t++) {
-            const ge_niels* tab;
+            int tab;
             sc s;
-            if (t == 0) { tab = C->fb[ACT_BASE_H3]; s = load_scalar(pf + 8 * (268 + 2 * j + b)); }
-            else if (t == 1) { if (!b) continue; tab = C->fb[ACT_BASE_H1]; s = sc_sub(load_scalar(pf + 8 * 132), load_scalar(pf + 8 * (140 + j))); }
-            else { if (j != 0) continue; tab = C->fb[ACT_BASE_H2]; s = load_scalar(pf + 8 * (138 + b)); }
-            Q = fb_accumulate(Q, tab, sc_half(s), false);
+            if (t == 0) { tab = ACT_BASE_H3; s = load_scalar(pf + 8 * (268 + 2 * j + b)); }
+            else if (t == 1) { if (!b) continue; tab = ACT_BASE_H1; s = sc_sub(load_scalar(pf + 8 * 132), load_scalar(pf + 8 * (140 + j))); }
+            else { if (j != 0) continue; tab = ACT_BASE_H2; s = load_scalar(pf + 8 * (138 + b)); }
+            Q = fb_accumulate(Q, C->fb[tab], sc_half(s), false);
         }
         store_fe(cp + 32 * b, Q.X); store_fe(cp + 32 * b + 8, Q.Y); store_fe(cp + 32 * b + 16, Q.Z); store_fe(cp + 32 * b + 24, Q.T);
     }
@@ -732,15 +745,16 @@ ACT_FN void build_table_thread(const ge* B, int win, ge_niels* tab) {
         Q = ge_add_cached(Q, Pc);
     }
 }
-// The wide-window tables: thread (win, part) writes entries part*N+1 .. part*N+N (N = (ENT-1)/PARTS) of window `win`,
-// converting to affine with one field inversion per ACT_FB_BATCH points (Montgomery's trick).  Part 0 also writes
-// the identity entry 0.
-ACT_FN void build_fb_table_thread(const ge* B, int win, int part, ge_niels* tab) {
-    const int N = (ACT_FB_ENT - 1) / ACT_FB_PARTS;
+// The wide-window tables: thread (win, part) writes entries part*N+1 .. part*N+N (N = ACT_FB_PART, or all of them for
+// narrow windows) of window `win`, converting to affine with one field inversion per ACT_FB_BATCH points (Montgomery's
+// trick).  Part 0 also writes the identity entry 0.
+ACT_FN void build_fb_table_thread(const ge* B, u32 bits, int win, int part, ge_niels* tab) {
+    const u32 ent = fb_ent_of(bits);
+    const int N = (int)((ent - 1) / fb_parts_of(bits));
     ge P = *B;
-    ACT_NOUNROLL for (int i = 0; i < ACT_FB_BITS * win; i++) P = ge_dbl(P, true);
+    ACT_NOUNROLL for (int i = 0; i < (int)bits * win; i++) P = ge_dbl(P, true);
     ge_cached Pc = ge_to_cached(P);
-    ge_niels* row = tab + (size_t)win * ACT_FB_ENT;
+    ge_niels* row = tab + (size_t)win * ent;
     if (part == 0) row[0] = ge_niels_identity();
     // Q = (part * N) * P : N is a power of two
     ge Q = ge_identity();
@@ -763,7 +777,7 @@ ACT_FN void build_fb_table_thread(const ge* B, int win, int part, ge_niels* tab)
         ACT_NOUNROLL for (int i = ACT_FB_BATCH - 1; i >= 0; i--) {
             fe zi = fe_mul(inv, prefix[i]);
             inv = fe_mul(inv, zs[i]);
-            row[part * N + k0 + i + 1] = ge_affine_to_niels(fe_mul(xs[i], zi), fe_mul(ys[i], zi));
+            row[(size_t)part * N + k0 + i + 1] = ge_affine_to_niels(fe_mul(xs[i], zi), fe_mul(ys[i], zi));
         }
     }
 }

@@ -119,12 +119,26 @@ __global__ void setup_decode_kernel(const u32* enc /* 4 x 8 words: H1,H2,H3,W */
     }
 }
 // the wide-window tables of G, H1, H2, H3: one thread per (base, window, part)
-__global__ void build_fb_tables_kernel(const ge* bases, ge_niels* tabs) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < 4 * ACT_FB_WIN * ACT_FB_PARTS) {
-        int part = t % ACT_FB_PARTS, win = (t / ACT_FB_PARTS) % ACT_FB_WIN, base = t / (ACT_FB_PARTS * ACT_FB_WIN);
-        build_fb_table_thread(&bases[base], win, part, tabs + (size_t)base * ACT_FB_SIZE);
+struct fb_layout { u32 bits[4]; u32 first_thread[5]; size_t offset[4]; };
+__global__ void build_fb_tables_kernel(const ge* bases, ge_niels* tabs, fb_layout L) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.first_thread[4]) return;
+    int base = 0;
+    while (t >= L.first_thread[base + 1]) base++;
+    u32 r = t - L.first_thread[base], parts = fb_parts_of(L.bits[base]);
+    build_fb_table_thread(&bases[base], L.bits[base], (int)(r / parts), (int)(r % parts), tabs + L.offset[base]);
+}
+static fb_layout make_fb_layout(size_t* total_entries) {
+    fb_layout L;
+    const u32 bits[4] = {ACT_FB_BITS, ACT_FB_BITS_HOT, ACT_FB_BITS, ACT_FB_BITS_HOT};   // G, H1, H2, H3
+    size_t off = 0; u32 th = 0;
+    for (int b = 0; b < 4; b++) {
+        L.bits[b] = bits[b]; L.offset[b] = off; L.first_thread[b] = th;
+        off += fb_size_of(bits[b]); th += fb_win_of(bits[b]) * fb_parts_of(bits[b]);
     }
+    L.first_thread[4] = th;
+    *total_entries = off;
+    return L;
 }
 __global__ void build_ct_table_kernel(const ge* bases, ge_niels* tab) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,7 +387,9 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         CKB(cudaEventCreateWithFlags(&e->join[0], cudaEventDisableTiming));
         CKB(cudaEventCreateWithFlags(&e->join[1], cudaEventDisableTiming));
         CKB(cudaMalloc((void**)&e->d_ctx, sizeof(act_ctx)));
-        CKB(cudaMalloc((void**)&e->d_tables, sizeof(ge_niels) * (4 * (size_t)ACT_FB_SIZE + ACT_CT_SIZE)));
+        size_t fb_entries = 0;
+        fb_layout L = make_fb_layout(&fb_entries);
+        CKB(cudaMalloc((void**)&e->d_tables, sizeof(ge_niels) * (fb_entries + ACT_CT_SIZE)));
         CKB(cudaMalloc((void**)&e->d_bases, sizeof(ge) * 4));
         CKB(cudaMalloc((void**)&d_enc, 128));
         CKB(cudaMalloc((void**)&d_ok, 4));
@@ -381,8 +397,8 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         CKB(cudaMemcpy(d_enc, h, 96, cudaMemcpyHostToDevice));
         CKB(cudaMemcpy(d_enc + 24, pk_w, 32, cudaMemcpyHostToDevice));
         setup_decode_kernel<<<1, 1>>>(d_enc, e->d_bases, d_W, d_ok);
-        build_fb_tables_kernel<<<(4 * ACT_FB_WIN * ACT_FB_PARTS + 31) / 32, 32>>>(e->d_bases, e->d_tables);
-        build_ct_table_kernel<<<1, ACT_CT_WIN>>>(e->d_bases, e->d_tables + 4 * (size_t)ACT_FB_SIZE);
+        build_fb_tables_kernel<<<(L.first_thread[4] + 31) / 32, 32>>>(e->d_bases, e->d_tables, L);
+        build_ct_table_kernel<<<1, ACT_CT_WIN>>>(e->d_bases, e->d_tables + fb_entries);
         CKB(cudaGetLastError());
         u32 ok = 0;
         CKB(cudaMemcpy(&ok, d_ok, 4, cudaMemcpyDeviceToHost));
@@ -390,8 +406,8 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         // context
         act_ctx hc;
         memset(&hc, 0, sizeof hc);
-        for (int b = 0; b < 4; b++) hc.fb[b] = e->d_tables + (size_t)b * ACT_FB_SIZE;
-        hc.ct_g = e->d_tables + 4 * (size_t)ACT_FB_SIZE;
+        for (int b = 0; b < 4; b++) { hc.fb[b].p = e->d_tables + L.offset[b]; hc.fb[b].bits = L.bits[b]; hc.fb[b].win = fb_win_of(L.bits[b]); hc.fb[b].ent = fb_ent_of(L.bits[b]); }
+        hc.ct_g = e->d_tables + fb_entries;
         memcpy(hc.h_enc, h, 96);
         build_prefix(&hc, ACT_TR_REQUEST, "request", h);
         build_prefix(&hc, ACT_TR_RESPOND, "respond", h);
