@@ -84,6 +84,7 @@ struct act_ctx {
     const ge_niels* ct_g;    // constant-time table for G
     sc x;                    // issuer secret
     ge W;                    // issuer public key
+    ge W_half;               // (1/2 mod l) * W: lets X_G = G*e + W be produced as a half for the batched encode
     u32 h_enc[3][8];         // encodings of H1..H3
     u32 prefix[4][48];       // transcript prefixes "request","respond","refund","spend" as LE words, zero padded
     u32 prefix_len[4];       // 186, 186, 185, 184 bytes
@@ -317,6 +318,15 @@ ACT_NOINLINE void vb_mul_ct_(ge* out, const ge* P, const sc* s) {
     *out = acc;
 }
 
+// engine set-up: reduce the stored secret mod l (Scalar::from_bytes_mod_order semantics for the key) and precompute W/2
+ACT_FN void ctx_finalize_thread(act_ctx* C) {
+    C->x = sc_from_words(C->x.v);
+    vb_table t;
+    vb_table_build(&t, C->W);
+    sc one = sc_from_u32(1);
+    C->W_half = vb_mul(&t, sc_half(one), false);     // W is public
+}
+
 // ---- single-chunk transcripts ---------------------------------------------------------------------------
 struct tr_small { u32 buf[128]; u32 len; };  // up to 512 bytes
 
@@ -345,30 +355,56 @@ ACT_FN sc tr_challenge(tr_small* t) {
 // =============================================================================================================
 // BBS signing tail shared by issue and refund (src/lib.rs:643-662 and :846-868)
 // =============================================================================================================
+// encode(2 * P_i) for four points with ONE field inversion (double-and-encode, ge25519.cuh): the signing tail produces
+// A, X_G, Y_A, Y_G as halves (every scalar involved is known to the signer and gets halved), which replaces four inverse
+// square roots (4 x 254 squarings) by one inversion.  Branch-free: the points depend on the issuer's secrets.
+ACT_NOINLINE void encode4_doubled_(u32* out /* 4 x 8 words */, const ge* pts /* 4 */) {
+    fe prefix[4], ts[4];
+    fe acc = fe_one();
+    ACT_NOUNROLL for (int i = 0; i < 4; i++) {
+        ge_dbl_enc s = ge_dbl_enc_prepare(pts[i]);
+        fe t = fe_mul(s.eg, s.fh);
+        t = fe_select(t, fe_one(), fe_is_zero(t));
+        prefix[i] = acc; ts[i] = t;
+        acc = fe_mul(acc, t);
+    }
+    fe inv = fe_invert(acc);
+    ACT_NOUNROLL for (int i = 3; i >= 0; i--) {
+        ge_dbl_enc s = ge_dbl_enc_prepare(pts[i]);
+        u32 zero = fe_is_zero(fe_mul(s.eg, s.fh));
+        fe inv_i = fe_mul(inv, prefix[i]);
+        inv = fe_mul(inv, ts[i]);
+        u32 w[8];
+        ge_dbl_enc_finish(w, s, inv_i);
+        u32 m = 0u - (zero ^ 1u);                                  // 2P in the identity coset encodes as 32 zero bytes
+        ACT_UNROLL for (int k = 0; k < 8; k++) out[8 * i + k] = w[k] & m;
+    }
+}
 // X_A given; rnd = 32 words (e_wide || alpha_wide).  kind = ACT_TR_RESPOND (c, e, points) or ACT_TR_REFUND (e, points).
 // Writes A (8 words), e, gamma, z.
 ACT_NOINLINE void bbs_sign_(const act_ctx* C, const ge* X_A, const u32* rnd, int kind, const sc* c,
                             u32* A_enc, sc* e_out, sc* gamma_out, sc* z_out) {
     sc e = sc_from_wide(rnd);
     sc ex = sc_add(e, C->x);
-    sc inv = sc_invert(ex);
-    ge A;
-    vb_mul_ct_(&A, X_A, &inv);                                   // A = X_A * (e+x)^-1        [secret scalar]
-    ge X_G = fb_accumulate(C->W, C->fb[ACT_BASE_G], e, false);   // X_G = G*e + W             [e is public output]
+    sc inv = sc_half(sc_invert(ex));
+    ge P[4];                                                         // halves of A, X_G, Y_A, Y_G
+    vb_mul_ct_(&P[0], X_A, &inv);                                    // A = X_A * (e+x)^-1        [secret scalar]
+    P[1] = fb_accumulate(C->W_half, C->fb[ACT_BASE_G], sc_half(e), false);   // X_G = G*e + W     [e is public output]
     sc alpha = sc_from_wide(rnd + 16);
-    ge Y_A;
-    vb_mul_ct_(&Y_A, &A, &alpha);                                // Y_A = A * alpha           [secret scalar]
-    ge Y_G = fb_accumulate_ct(ge_identity(), C->ct_g, alpha);    // Y_G = G * alpha           [secret scalar]
+    vb_mul_ct_(&P[2], &P[0], &alpha);                                // Y_A = A * alpha           [secret scalar]
+    sc ah = sc_half(alpha);
+    P[3] = fb_accumulate_ct(ge_identity(), C->ct_g, ah);             // Y_G = G * alpha           [secret scalar]
+    u32 enc[32];
+    encode4_doubled_(enc, P);
     tr_small tr;
     tr_init(&tr, C, kind);
     if (kind == ACT_TR_RESPOND) tr_add32(&tr, c->v);
     tr_add32(&tr, e.v);
     u32 w[8];
-    ristretto_encode_(A_enc, &A); tr_add32(&tr, A_enc);
+    ACT_UNROLL for (int k = 0; k < 8; k++) A_enc[k] = enc[k];
+    tr_add32(&tr, A_enc);
     ristretto_encode_(w, X_A); tr_add32(&tr, w);
-    ristretto_encode_(w, &X_G); tr_add32(&tr, w);
-    ristretto_encode_(w, &Y_A); tr_add32(&tr, w);
-    ristretto_encode_(w, &Y_G); tr_add32(&tr, w);
+    tr_add32(&tr, enc + 8); tr_add32(&tr, enc + 16); tr_add32(&tr, enc + 24);
     sc gamma = tr_challenge(&tr);
     *e_out = e; *gamma_out = gamma;
     *z_out = sc_add(sc_mul(gamma, ex), alpha);                   // z = gamma*(x+e) + alpha

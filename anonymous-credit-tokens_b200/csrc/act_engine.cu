@@ -144,9 +144,9 @@ __global__ void build_ct_table_kernel(const ge* bases, ge_niels* tab) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < ACT_CT_WIN) build_table_thread<4, ACT_CT_ENT>(&bases[0], t, tab);
 }
-// reduce the stored secret mod l once (Scalar::from_bytes_mod_order semantics for the key)
+// reduce the stored secret mod l once and precompute W/2
 __global__ void finalize_ctx_kernel(act_ctx* C) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) C->x = sc_from_words(C->x.v);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctx_finalize_thread(C);
 }
 __global__ void public_key_kernel(const ge_niels* ct_g, const u32* x, u32* out) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {

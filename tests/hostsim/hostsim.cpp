@@ -64,8 +64,8 @@ EXPORT hs_ctx* hs_ctx_create(const uint8_t h[96], const uint8_t x[32], const uin
     build_prefix(&H->c, ACT_TR_RESPOND, "respond", h);
     build_prefix(&H->c, ACT_TR_REFUND, "refund", h);
     build_prefix(&H->c, ACT_TR_SPEND, "spend", h);
-    memcpy(words, x, 32);
-    H->c.x = sc_from_words(words);
+    memcpy(H->c.x.v, x, 32);
+    ctx_finalize_thread(&H->c);
     return H;
 }
 EXPORT void hs_ctx_destroy(hs_ctx* H) { delete H; }
