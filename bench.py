@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--n-issue", type=int, default=1 << 20, help="IssuanceRequests per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mixed-frac", type=float, default=0.1, help="tampered fraction of the mixed adversarial batch (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -365,6 +366,42 @@ def main():
     assert (o_ist == 0).all() and (d_resp[:8 * 160].cpu().numpy() == o_resp).all(), "issue output differs from oracle"
     issue_value = world * ni * K / (ims * 1e-3)
 
+    # ---- mixed adversarial batch (BASELINE configs[4] shape): the same n proofs with a fraction tampered on the device, one
+    # class per row of the mutation table, the expected status of every index known by construction;
+    # then the engine's replay screen over the batch.  Timed like `value`; the un-tampered batch is restored afterwards. ----
+    mixed = None
+    if args.mixed_frac > 0:
+        pv = d_proofs.view(n, PROOF_BYTES)
+        sel = torch.rand(n, device=dev, generator=gen) < args.mixed_frac
+        sel[0] = False
+        tidx = torch.nonzero(sel).view(-1)
+        cls = torch.randint(0, 5, (tidx.numel(),), device=dev, generator=gen)
+        saved = pv[tidx].clone()
+        expect = torch.zeros(n, dtype=torch.uint8, device=dev)
+        i0 = tidx[cls == 0]; pv[i0, 32] ^= 1; expect[i0] = 7                      # s changed            -> InvalidClientSpendProof
+        i1 = tidx[cls == 1]; pv[i1, 64:96] = 0; expect[i1] = 6                    # A' = identity        -> IdentityPointError
+        bad = torch.tensor(list(((1 << 255) - 19).to_bytes(32, "little")), dtype=torch.uint8, device=dev)
+        i2 = tidx[cls == 2]; pv[i2, 128 + 32 * 77:128 + 32 * 78] = bad; expect[i2] = 0x81   # com[77] = non-canonical p -> decode error
+        i3 = tidx[cls == 3]; pv[i3, 32 * 132 + 3] ^= 0x40; expect[i3] = 7          # gamma bit flip       -> InvalidClientSpendProof
+        i4 = tidx[cls == 4]; pv[i4] = pv[i4 - 1]                                   # replay of the neighbour (still Ok for refund())
+        expect[i4] = expect[i4 - 1]
+        mms = timed(spend_step, 1, K)
+        st_m = d_st.clone()
+        ok_status = bool((st_m == expect).all())
+        d_flag = torch.empty_like(d_st)
+        eng.flag_replays_dev(n, d_st.data_ptr(), d_nul.data_ptr(), 0, None, d_flag.data_ptr(), stream)
+        torch.cuda.synchronize()
+        replays = int((d_flag == 3).sum().item())
+        mixed = {"value": world * n * K / (mms * 1e-3), "unit": UNIT, "tampered_fraction": float(sel.float().mean().item()),
+                 "classes": "s changed, A' identity, malformed com point, gamma bit flip, replayed proof (uniform)",
+                 "status_matches_expectation": ok_status, "accepted": int((st_m == 0).sum().item()),
+                 "rejected_by_status": {str(k): int((st_m == k).sum().item()) for k in (6, 7, 0x81)},
+                 "replays_flagged_by_screen": replays, "replays_planted_valid": int(((expect[i4] == 0) & (expect[i4 - 1] == 0)).sum().item())}
+        assert ok_status, "mixed batch: a status differs from the class's expected status"
+        pv[tidx] = saved
+        del saved, st_m, d_flag, expect
+        torch.cuda.synchronize()
+
     # ---- e2e: pinned host buffers through the public C ABI (H2D + kernels + D2H inside the timed region) ----
     Ke = args.e2e_steps or K
     host_mem = "pinned"
@@ -429,6 +466,7 @@ def main():
                       "workload": f"batch_issue of {ni} IssuanceRequests per GPU (BASELINE configs[1])",
                       "e2e": {"value": world * ni * Ke / e2e_issue_s, "h2d_bytes_per_step": ni * 288, "d2h_bytes_per_step": ni * 161},
                       "roofline_frac": LIMB_MACS_PER_ISSUE * issue_value / world / peak},
+            "mixed_adversarial": mixed,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
