@@ -177,6 +177,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version banner to fd 1) write to stderr instead.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import corpus
@@ -472,7 +476,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out), flush=True)
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
