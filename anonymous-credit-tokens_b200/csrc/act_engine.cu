@@ -145,8 +145,16 @@ __global__ void build_ct_table_kernel(const ge* bases, ge_niels* tab) {
     if (t < ACT_CT_WIN) build_table_thread<4, ACT_CT_ENT>(&bases[0], t, tab);
 }
 // reduce the stored secret mod l once and precompute W/2
-__global__ void finalize_ctx_kernel(act_ctx* C) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctx_finalize_thread(C);
+// ... and check that the public key given is the public key of the secret: ok = (encode(G*x) == encode(W))
+__global__ void finalize_ctx_kernel(act_ctx* C, const u32* w_enc, u32* ok) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctx_finalize_thread(C);
+        ge W = fb_accumulate_ct(ge_identity(), C->ct_g, C->x);
+        u32 enc[8], same = 1;
+        ristretto_encode_(enc, &W);
+        for (int i = 0; i < 8; i++) same &= (enc[i] == w_enc[i]);
+        *ok = same;
+    }
 }
 __global__ void public_key_kernel(const ge_niels* ct_g, const u32* x, u32* out) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -418,9 +426,11 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         memcpy(hc.x.v, sk_x, 32);
         CKB(cudaMemcpy(e->d_ctx, &hc, sizeof hc, cudaMemcpyHostToDevice));
         memset(&hc, 0, sizeof hc);
-        finalize_ctx_kernel<<<1, 1>>>(e->d_ctx);
+        finalize_ctx_kernel<<<1, 1>>>(e->d_ctx, d_enc + 24, d_ok);
         CKB(cudaGetLastError());
         CKB(cudaDeviceSynchronize());
+        CKB(cudaMemcpy(&ok, d_ok, 4, cudaMemcpyDeviceToHost));
+        if (!ok) { rc = fail_msg("act_engine_create: pk_w is not the public key of sk_x (W != G*x)"); break; }
 #undef CKB
     } while (0);
     cudaFree(d_enc); cudaFree(d_ok); cudaFree(d_W);

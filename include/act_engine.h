@@ -79,7 +79,7 @@ ACT_API int act_params_derive(int device, const char* org, const char* service, 
                       uint8_t h[96]);
 
 /* Engine for one (Params, PrivateKey) pair on one GPU.  h = H1|H2|H3 encodings, sk_x = secret scalar
- * (reduced mod l), pk_w = encoding of W = G*x.  Fails if any point does not decode. */
+ * (reduced mod l), pk_w = encoding of W = G*x.  Fails if any point does not decode or if pk_w is not G*sk_x. */
 ACT_API int act_engine_create(act_engine** out, int device, const uint8_t h[96], const uint8_t sk_x[32], const uint8_t pk_w[32]);
 /* Zeroises the device and host copies of the secret and frees everything. */
 ACT_API void act_engine_destroy(act_engine* e);

@@ -376,3 +376,19 @@ def test_sequential_rng_contract(engine, octx, base):
     full_rnd = np.zeros((N, 128), np.uint8); full_rnd[acc] = packed
     r3, n3, s3 = engine.batch_verify_spend_and_refund(P, full_rnd.reshape(-1))
     assert (r3 == r2).all() and (n3 == n2).all() and (s3 == s2).all()
+
+
+def test_engine_rejects_inconsistent_key_and_bad_params(act, octx):
+    """act_engine_create fails loudly: W that is not G*x, undecodable H or W."""
+    x2, w2 = O.keygen(corpus.xof(b"other-key", 64))
+    with pytest.raises(act.ActError):
+        act.Engine(act.Params(octx.h), act.PrivateKey(octx.x, w2))
+    bad = bytearray(octx.h); bad[0:32] = corpus.bad_point_encodings()[0]
+    with pytest.raises(act.ActError):
+        act.Engine(act.Params(bytes(bad)), act.PrivateKey(octx.x, octx.w))
+    with pytest.raises(act.ActError):
+        act.Engine(act.Params(octx.h), act.PrivateKey(octx.x, corpus.bad_point_encodings()[4]))
+    # a non-canonical secret (x + l) is the same key
+    xl = (corpus.sc_int(octx.x) + corpus.ELL).to_bytes(32, "little")
+    with act.Engine(act.Params(octx.h), act.PrivateKey(xl, octx.w)) as e:
+        assert e.launch_count > 0
