@@ -136,7 +136,7 @@ def run_reference(args, rank, world):
     import corpus
     threads = os.cpu_count() or 1
     ctx = corpus.make_ctx(corpus.BENCH_PARAMS)
-    n = max(threads * 2, 64)
+    n = max(threads * 32, 256)   # per step: enough calls per thread that thread start-up and imbalance do not show
     base = corpus.gen_valid(ctx, n, seed=b"bench-spend", credits=(20, 1000), threads=threads)
     times = []
     for s in range(args.warmup + args.steps):
