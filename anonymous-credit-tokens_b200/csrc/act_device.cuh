@@ -291,7 +291,15 @@ ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
     ge a = ge_identity();
     ACT_NOUNROLL for (int i = WIN - 1; i >= 0; i--) {
         if (i != WIN - 1) {
-            ACT_NOUNROLL for (int d = 0; d < 4; d++) a = ge_dbl_u(a, d == 3);
+            ACT_NOUNROLL for (int d = 0; d < 4; d++) {
+#if ACT_PREFETCH >= 2
+                if (d == 3) {   // the first table's entry of this window travels during the last doubling
+                    int d0 = sc_digit<4>(b, i);
+                    prefetch_line(&t[0].e[d0 < 0 ? -d0 : d0]);
+                }
+#endif
+                a = ge_dbl_u(a, d == 3);
+            }
         }
         ACT_NOUNROLL for (int k = 0; k < M; k++) {
             if (k + 1 < M) {   // the next table's entry travels to L1 while this addition runs
