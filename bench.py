@@ -109,6 +109,10 @@ def synth(ctx, n_unique_proofs, n_unique_req, threads):
 
 def cpu_baseline(ctx, base, reqs, threads, budget_s=8.0):
     """Oracle (restated reference algorithm) on the host cores: typed refund()/issue() closures as in benches/benchmark.rs."""
+    import corpus
+    import oracle_lib
+    if oracle_lib.use_native_build():      # time the -march=native build of the port; a new context binds to it
+        ctx = corpus.make_ctx(corpus.BENCH_PARAMS)
     n1 = 24
     t1, ok = ctx.time_refund_typed(base["proofs"][:n1 * PROOF_BYTES], base["rnd"][:n1 * 128], threads=1, reps=1)
     assert ok == n1
@@ -135,6 +139,8 @@ def run_reference(args, rank, world):
         return
     import corpus
     threads = os.cpu_count() or 1
+    import oracle_lib
+    native = oracle_lib.use_native_build()
     ctx = corpus.make_ctx(corpus.BENCH_PARAMS)
     n = max(threads * 32, 256)   # per step: enough calls per thread that thread start-up and imbalance do not show
     base = corpus.gen_valid(ctx, n, seed=b"bench-spend", credits=(20, 1000), threads=threads)

@@ -36,6 +36,21 @@ def build(force=False):
 _lib = None
 
 
+def use_native_build():
+    """bench.py's CPU-baseline legs: rebuild the oracle with -march=native on the machine it is timed on (the shipped .so is
+    compiled for a portable x86-64-v2 target because it travels to the GPU box).  Falls back silently to the portable build."""
+    global _SO, _lib
+    native = os.path.join(ORACLE_DIR, "libact_oracle_native.so")
+    try:
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        if os.path.exists(native):
+            _SO, _lib = native, None
+            return True
+    except Exception:
+        pass
+    return False
+
+
 def lib():
     global _lib
     if _lib is None:
