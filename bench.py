@@ -142,7 +142,7 @@ def run_reference(args, rank, world):
     import oracle_lib
     native = oracle_lib.use_native_build()
     ctx = corpus.make_ctx(corpus.BENCH_PARAMS)
-    n = max(threads * 32, 256)   # per step: enough calls per thread that thread start-up and imbalance do not show
+    n = max(threads * 64, 512)   # per step: enough calls per thread that thread start-up and imbalance do not show
     base = corpus.gen_valid(ctx, n, seed=b"bench-spend", credits=(20, 1000), threads=threads)
     times = []
     for s in range(args.warmup + args.steps):
