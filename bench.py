@@ -470,11 +470,11 @@ def main():
                        "fixtures": f"{n} unique tokens per GPU requested, issued and spent on the device by the engine's generators (bit-exact with the oracle prover); charges uniform in [1, c-1], c in [20, 1000)",
                        "l2": "inputs (17.6 GB per step) far larger than L2; no flush needed",
                        "collective": "all_gather of status+nullifiers (33 B/proof) inside the step" if world > 1 else "none (single GPU)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (PROOF_BYTES + 128), "d2h_bytes_per_step": n * 161, "steps": Ke,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * n * (PROOF_BYTES + 128), "d2h_bytes_per_step": world * n * 161, "steps": Ke,
                     "api": f"act_batch_verify_spend_and_refund (C ABI, {host_mem} host buffers)"},
             "issue": {"metric": "issues_per_sec", "value": issue_value, "unit": "issues/s", "ms_per_step": ims / K, "n": ni,
                       "workload": f"batch_issue of {ni} IssuanceRequests per GPU (BASELINE configs[1])",
-                      "e2e": {"value": world * ni * Ke / e2e_issue_s, "h2d_bytes_per_step": ni * 288, "d2h_bytes_per_step": ni * 161},
+                      "e2e": {"value": world * ni * Ke / e2e_issue_s, "h2d_bytes_per_step": world * ni * 288, "d2h_bytes_per_step": world * ni * 161},
                       "roofline_frac": LIMB_MACS_PER_ISSUE * issue_value / world / peak},
             "mixed_adversarial": mixed,
             "gpu_launches": int(launches),
