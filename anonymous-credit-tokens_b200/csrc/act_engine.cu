@@ -51,10 +51,73 @@ __global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issuance_check_kernel(cons
 #ifndef ACT_RANGE_BLOCKS_PER_SM
 #define ACT_RANGE_BLOCKS_PER_SM 4   // 128 registers per thread; measured 153k vs 146k proofs/s at 3
 #endif
-__global__ void __launch_bounds__(ACT_L, ACT_RANGE_BLOCKS_PER_SM) spend_range_kernel(const act_ctx* C, size_t m, const u32* proofs, u32* items, u32* com_niels, u32* flags, vb_table* tabs, u32* cpts) {
-    vb_table* mine = tabs + ((size_t)blockIdx.x * ACT_L + threadIdx.x) * ACT_RANGE_SPLIT;
-    for (size_t p = blockIdx.x; p < m; p += gridDim.x) spend_range_thread(C, p, threadIdx.x, proofs, items, com_niels, flags, mine, cpts);
+// Work distribution: the unit of work is one warp's quarter of a proof (32 of its 128 com_j).  Every resident warp draws
+// the next unit from a per-launch counter.  Measured on B200 (profiles/r01i_range_trace.txt): with a static grid-stride
+// assignment of whole proofs to blocks, the warps of one SM finish the SAME amount of work between 60 ms and 96 ms after
+// launch -- the warp scheduler is not fair between warps -- so on average only 79 % of the launched warps were resident;
+// drawing units on demand keeps 98 % resident (a favoured warp simply draws up to 3x the units of a starved one) and
+// also spreads the two extra fixed-base terms of lane j = 0.  ACT_RANGE_DYNAMIC=0 is the static form (block = 128 only).
+#ifndef ACT_RANGE_DYNAMIC
+#define ACT_RANGE_DYNAMIC 1
+#endif
+// threads per block of the range kernel (a multiple of 32; the unit of work is a warp, so any block size works in the
+// dynamic form) and resident blocks per SM
+#ifndef ACT_RANGE_BLOCK
+#define ACT_RANGE_BLOCK 128
+#endif
+#if !ACT_RANGE_DYNAMIC && ACT_RANGE_BLOCK != ACT_L
+#error "the static work distribution needs one block per proof"
+#endif
+#define ACT_RANGE_UNITS (ACT_L / 32)    // units per proof
+#if ACT_RANGE_TRACE
+__device__ unsigned long long act_trace_buf[4096 * 4];   // per warp: smid, first/last globaltimer, units
+__device__ __forceinline__ unsigned long long act_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+#ifdef ACT_RANGE_MAXREG   // explicit register cap instead of a resident-block target (block sizes of 32/64 threads)
+#define ACT_RANGE_BOUNDS __maxnreg__(ACT_RANGE_MAXREG)
+#else
+#define ACT_RANGE_BOUNDS __launch_bounds__(ACT_RANGE_BLOCK, ACT_RANGE_BLOCKS_PER_SM)
+#endif
+__global__ void ACT_RANGE_BOUNDS spend_range_kernel(const act_ctx* C, size_t m, const u32* proofs, u32* items, u32* com_niels, u32* flags, vb_table* tabs, u32* cpts, u32* counter) {
+    vb_table* mine = tabs + ((size_t)blockIdx.x * ACT_RANGE_BLOCK + threadIdx.x) * ACT_RANGE_SPLIT;
+#if ACT_RANGE_TRACE
+    unsigned long long t0 = act_gtime(), units = 0;
+#endif
+#if ACT_RANGE_DYNAMIC
+    const u32 lane = threadIdx.x & 31u, total = (u32)m * ACT_RANGE_UNITS;
+    for (;;) {
+        u32 unit = 0;
+        if (lane == 0) unit = atomicAdd(counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= total) break;
+        spend_range_thread(C, unit / ACT_RANGE_UNITS, (int)((unit % ACT_RANGE_UNITS) * 32 + lane), proofs, items, com_niels, flags, mine, cpts);
+#if ACT_RANGE_TRACE
+        units++;
+#endif
+    }
+#else
+    (void)counter;
+    for (size_t p = blockIdx.x; p < m; p += gridDim.x) {
+        spend_range_thread(C, p, threadIdx.x, proofs, items, com_niels, flags, mine, cpts);
+#if ACT_RANGE_TRACE
+        units++;
+#endif
+    }
+#endif
+#if ACT_RANGE_TRACE
+    if ((threadIdx.x & 31) == 0) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned w = blockIdx.x * (ACT_RANGE_BLOCK / 32) + threadIdx.x / 32;
+        if (w < 4096) { act_trace_buf[4 * w] = smid; act_trace_buf[4 * w + 1] = t0; act_trace_buf[4 * w + 2] = act_gtime(); act_trace_buf[4 * w + 3] = units; }
+    }
+#endif
 }
+#if ACT_RANGE_TRACE
+// dev tool (tools/trace_range.py): not part of the ABI, only present in builds with -DACT_RANGE_TRACE=1
+extern "C" __attribute__((visibility("default"))) int act_debug_read_trace(unsigned long long* out, size_t n) {
+    return (int)cudaMemcpyFromSymbol(out, act_trace_buf, n * sizeof(unsigned long long));
+}
+#endif
 // encodes the 256 commitments of each proof: one thread per 16 points (batched inversion)
 #define ACT_ENC_BLOCK 128
 #define ACT_ENC_PARTS (2 * ACT_L / ACT_ENC_BATCH)
@@ -231,13 +294,16 @@ static int fail_msg(const char* what) { g_err = what; return -1; }
         if (e_ != cudaSuccess) return fail(#call, e_); \
     } while (0)
 
+#ifndef ACT_SPEND_CHUNK
 #define ACT_SPEND_CHUNK 16384   // proofs per pipeline chunk
+#endif
 #define ACT_SMALL_CHUNK 262144  // requests per chunk for the light-weight paths
 
 struct spend_scratch {
     u32 *items = nullptr, *com_niels = nullptr, *kprime = nullptr, *flags = nullptr, *cvs = nullptr;
     u32* cpts = nullptr;        // half-commitments C'/2 in extended coordinates: m x 256 x 128 B
     vb_table* tabs = nullptr;   // window tables of the range kernel: grid x 128 threads x ACT_RANGE_SPLIT
+    u32* counter = nullptr;     // work counter of the range kernel (units drawn so far in the current launch)
     unsigned range_grid = 0;
     size_t cap = 0;
 };
@@ -290,10 +356,11 @@ static int ensure_scratch(spend_scratch* s, size_t n) {
         int dev = 0, sms = 0, per_sm = 0;
         CK(cudaGetDevice(&dev));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spend_range_kernel, ACT_L, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spend_range_kernel, ACT_RANGE_BLOCK, 0));
         if (per_sm < 1) per_sm = 1;
         s->range_grid = (unsigned)(sms * per_sm);
-        CK(cudaMalloc((void**)&s->tabs, (size_t)s->range_grid * ACT_L * ACT_RANGE_SPLIT * sizeof(vb_table)));
+        CK(cudaMalloc((void**)&s->tabs, (size_t)s->range_grid * ACT_RANGE_BLOCK * ACT_RANGE_SPLIT * sizeof(vb_table)));
+        CK(cudaMalloc((void**)&s->counter, 4));
     }
     if (s->cap >= n) return 0;
     cudaFree(s->items); cudaFree(s->com_niels); cudaFree(s->kprime); cudaFree(s->flags); cudaFree(s->cvs); cudaFree(s->cpts);
@@ -366,7 +433,7 @@ extern "C" void act_engine_destroy(act_engine* e) {
     for (int s = 0; s < 2; s++) if (e->join[s]) cudaEventDestroy(e->join[s]);
     for (int s = 0; s < 2; s++) {
         spend_scratch& sc_ = e->scratch[s];
-        cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs); cudaFree(sc_.tabs); cudaFree(sc_.cpts);
+        cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs); cudaFree(sc_.tabs); cudaFree(sc_.counter); cudaFree(sc_.cpts);
         io_slot& io = e->io[s];
         cudaFree(io.in0); cudaFree(io.in1); cudaFree(io.in2); cudaFree(io.out0); cudaFree(io.out1); cudaFree(io.st);
         if (e->stream[s]) cudaStreamDestroy(e->stream[s]);
@@ -597,8 +664,10 @@ extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* c
 static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, size_t m, const u32* proofs, const u32* rnd,
                               u32* refunds, u32* nullifiers, u8* status, u32* kprime_out = nullptr) {
     CK(cudaMemsetAsync(s->flags, 0, m * 4, st));
-    unsigned rgrid = m < s->range_grid ? (unsigned)m : s->range_grid;
-    LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<rgrid, ACT_L, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->flags, s->tabs, s->cpts)));
+    CK(cudaMemsetAsync(s->counter, 0, 4, st));
+    size_t rblocks = (m * ACT_L + ACT_RANGE_BLOCK - 1) / ACT_RANGE_BLOCK;   // blocks that would hold one thread per com_j
+    unsigned rgrid = rblocks < s->range_grid ? (unsigned)rblocks : s->range_grid;
+    LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<rgrid, ACT_RANGE_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->flags, s->tabs, s->cpts, s->counter)));
     LAUNCH(e, K_ENCODE, st, (spend_encode_kernel<<<nblocks(m * ACT_ENC_PARTS, ACT_ENC_BLOCK), ACT_ENC_BLOCK, 0, st>>>(e->d_ctx, m, s->cpts, s->items, 2 * ACT_L, 133)));
     u32* kp = kprime_out ? kprime_out : s->kprime;
     LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, kp, s->flags)));
