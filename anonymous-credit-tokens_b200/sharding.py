@@ -9,6 +9,8 @@ whole batch's accept bits.  Works with NCCL on GPU tensors and with gloo on CPU 
 import torch
 import torch.distributed as dist
 
+_SIDE = {}   # device -> side stream used when torch's current stream is the legacy default stream
+
 
 def shard_bounds(n, rank, world):
     """Contiguous range [lo, hi) of request indices owned by `rank`; sizes differ by at most one."""
@@ -53,8 +55,22 @@ def flag_replays(status, nullifiers, seen=None, engine=None):
         out = torch.empty_like(status)
         status, nullifiers = status.contiguous(), nullifiers.contiguous()
         k = 0 if seen is None else seen.numel() // 32
-        sp = seen.contiguous().data_ptr() if k else None
-        engine.flag_replays_dev(n, status.data_ptr(), nullifiers.data_ptr(), k, sp, out.data_ptr(), torch.cuda.current_stream(status.device).cuda_stream)
+        seen = seen.contiguous() if k else None
+        sp = seen.data_ptr() if k else None
+        cur = torch.cuda.current_stream(status.device)
+        if cur.cuda_stream != 0:
+            engine.flag_replays_dev(n, status.data_ptr(), nullifiers.data_ptr(), k, sp, out.data_ptr(), cur.cuda_stream)
+        else:
+            # torch is on the legacy default stream, whose handle (0) means "the engine's own stream" in the C ABI: run
+            # on a side stream ordered after the producers of the inputs and before the consumers of the result
+            side = _SIDE.get(status.device)
+            if side is None:
+                side = _SIDE[status.device] = torch.cuda.Stream(device=status.device)
+            side.wait_stream(cur)
+            engine.flag_replays_dev(n, status.data_ptr(), nullifiers.data_ptr(), k, sp, out.data_ptr(), side.cuda_stream)
+            for t in (status, nullifiers, out) + ((seen,) if k else ()):
+                t.record_stream(side)
+            cur.wait_stream(side)
         return out
     keys = nullifiers.view(n, 32).contiguous().view(torch.int64).view(n, 4)
     ok = status == 0

@@ -135,6 +135,21 @@ def test_golden_trip_and_corpus_on_gpu(act):
         assert (st == c["status"]).all() and (ref == c["refunds"]).all() and (nul == c["nullifiers"]).all()
 
 
+def test_ragged_sizes_around_the_resident_grid(engine, octx, base):
+    """The range kernel is persistent (SMs x resident blocks) and its warps draw quarter-proof units from a per-launch
+    counter: sizes below, at and just above the resident grid (592 blocks on B200), and sizes that are not a multiple of
+    anything, must give the tiled per-proof answers of the oracle bit for bit, call after call on the same engine."""
+    proofs, rnd, expect, labels = corpus.mutate_proofs(octx, base)
+    u = len(expect)
+    o_ref, o_nul, o_st, _ = octx.batch_refund(proofs, rnd, threads=8)
+    for n in (2, 3, 147, 591, 592, 593, 2369, 16385):
+        idx = (np.arange(n) * 5 + n) % u
+        P = proofs.reshape(u, -1)[idx].reshape(-1).copy(); R = rnd.reshape(u, -1)[idx].reshape(-1).copy()
+        ref, nul, st = engine.batch_verify_spend_and_refund(P, R)
+        assert (st == o_st[idx]).all(), n
+        assert (ref.reshape(n, -1) == o_ref.reshape(u, -1)[idx]).all() and (nul.reshape(n, -1) == o_nul.reshape(u, -1)[idx]).all(), n
+
+
 def test_large_mixed_adversarial_batch(engine, octx, base):
     """BASELINE config #5 shape at a size the GPU finishes in a second: 40 000 proofs, three quarters of them tampered
     (every mutation class of SURVEY section 4), crossing the 16 384-proof pipeline chunks and both streams with a ragged
