@@ -312,6 +312,7 @@ struct io_slot {  // device staging for the host-buffer entry points
     size_t cap_in0 = 0, cap_in1 = 0, cap_in2 = 0, cap_out0 = 0, cap_out1 = 0, cap_st = 0;
 };
 
+#define ACT_IO_SLOTS 3
 struct act_engine {
     int device = 0;
     cudaStream_t stream[2] = {nullptr, nullptr};
@@ -320,7 +321,11 @@ struct act_engine {
     ge_niels* d_tables = nullptr;
     ge* d_bases = nullptr;
     spend_scratch scratch[2];
-    io_slot io[2];
+    // host-buffer entry points: ACT_IO_SLOTS staging sets filled on a copy stream of their own, so that the H2D of chunk
+    // i+1 is already under way while chunk i computes and chunk i-1 drains (the two compute streams alternate as before)
+    io_slot io[ACT_IO_SLOTS];
+    cudaStream_t copy = nullptr;
+    cudaEvent_t io_ready[ACT_IO_SLOTS] = {}, io_done[ACT_IO_SLOTS] = {};
     uint64_t launches = 0;
     int32_t* d_skel[4] = {nullptr, nullptr, nullptr, nullptr};   // canonical CBOR skeletons (request, response, proof, refund)
     u32* d_rp_table = nullptr; size_t rp_cap = 0;                 // replay-screen hash table
@@ -434,10 +439,15 @@ extern "C" void act_engine_destroy(act_engine* e) {
     for (int s = 0; s < 2; s++) {
         spend_scratch& sc_ = e->scratch[s];
         cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs); cudaFree(sc_.tabs); cudaFree(sc_.counter); cudaFree(sc_.cpts);
-        io_slot& io = e->io[s];
-        cudaFree(io.in0); cudaFree(io.in1); cudaFree(io.in2); cudaFree(io.out0); cudaFree(io.out1); cudaFree(io.st);
         if (e->stream[s]) cudaStreamDestroy(e->stream[s]);
     }
+    for (int k = 0; k < ACT_IO_SLOTS; k++) {
+        io_slot& io = e->io[k];
+        cudaFree(io.in0); cudaFree(io.in1); cudaFree(io.in2); cudaFree(io.out0); cudaFree(io.out1); cudaFree(io.st);
+        if (e->io_ready[k]) cudaEventDestroy(e->io_ready[k]);
+        if (e->io_done[k]) cudaEventDestroy(e->io_done[k]);
+    }
+    if (e->copy) cudaStreamDestroy(e->copy);
     delete e;
 }
 
@@ -458,6 +468,12 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
 #define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
         CKB(cudaStreamCreateWithFlags(&e->stream[0], cudaStreamNonBlocking));
         CKB(cudaStreamCreateWithFlags(&e->stream[1], cudaStreamNonBlocking));
+        CKB(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+        for (int k = 0; k < ACT_IO_SLOTS && !rc; k++) {
+            if (cudaEventCreateWithFlags(&e->io_ready[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->io_done[k], cudaEventDisableTiming) != cudaSuccess) rc = fail_msg("cudaEventCreate (io slots)");
+        }
+        if (rc) break;
         CKB(cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming));
         CKB(cudaEventCreateWithFlags(&e->join[0], cudaEventDisableTiming));
         CKB(cudaEventCreateWithFlags(&e->join[1], cudaEventDisableTiming));
@@ -724,11 +740,11 @@ static int run_chunked(act_engine* e, size_t n, size_t chunk, const host_io& h, 
     CK(cudaSetDevice(e->device));
     size_t nchunks = (n + chunk - 1) / chunk;
     for (size_t ci = 0; ci < nchunks; ci++) {
-        int s = (int)(ci & 1);
-        io_slot& io = e->io[s];
+        int s = (int)(ci & 1), k = (int)(ci % ACT_IO_SLOTS);
+        io_slot& io = e->io[k];
         cudaStream_t st = e->stream[s];
         size_t off = ci * chunk, m = n - off < chunk ? n - off : chunk;
-        CK(cudaStreamSynchronize(st));  // slot reuse: previous chunk on this slot fully drained (incl. D2H)
+        if (ci >= ACT_IO_SLOTS) CK(cudaEventSynchronize(e->io_done[k]));  // slot reuse: chunk ci-3 fully drained (incl. D2H)
         int rc;
         if ((rc = ensure(&io.in0, &io.cap_in0, m * h.in_stride[0] + 16))) return rc;
         if (h.in[1] && (rc = ensure(&io.in1, &io.cap_in1, m * h.in_stride[1] + 16))) return rc;
@@ -736,13 +752,16 @@ static int run_chunked(act_engine* e, size_t n, size_t chunk, const host_io& h, 
         if (h.out[0] && (rc = ensure(&io.out0, &io.cap_out0, m * h.out_stride[0] + 16))) return rc;
         if (h.out[1] && (rc = ensure(&io.out1, &io.cap_out1, m * h.out_stride[1] + 16))) return rc;
         if ((rc = ensure(&io.st, &io.cap_st, m + 16))) return rc;
-        CK(cudaMemcpyAsync(io.in0, h.in[0] + off * h.in_stride[0], m * h.in_stride[0], cudaMemcpyHostToDevice, st));
-        if (h.in[1]) CK(cudaMemcpyAsync(io.in1, h.in[1] + off * h.in_stride[1], m * h.in_stride[1], cudaMemcpyHostToDevice, st));
-        if (h.in[2]) CK(cudaMemcpyAsync(io.in2, h.in[2] + off * h.in_stride[2], m * h.in_stride[2], cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(io.in0, h.in[0] + off * h.in_stride[0], m * h.in_stride[0], cudaMemcpyHostToDevice, e->copy));
+        if (h.in[1]) CK(cudaMemcpyAsync(io.in1, h.in[1] + off * h.in_stride[1], m * h.in_stride[1], cudaMemcpyHostToDevice, e->copy));
+        if (h.in[2]) CK(cudaMemcpyAsync(io.in2, h.in[2] + off * h.in_stride[2], m * h.in_stride[2], cudaMemcpyHostToDevice, e->copy));
+        CK(cudaEventRecord(e->io_ready[k], e->copy));
+        CK(cudaStreamWaitEvent(st, e->io_ready[k], 0));
         if ((rc = launch(s, st, m, io))) return rc;
         if (h.out[0]) CK(cudaMemcpyAsync(h.out[0] + off * h.out_stride[0], io.out0, m * h.out_stride[0], cudaMemcpyDeviceToHost, st));
         if (h.out[1]) CK(cudaMemcpyAsync(h.out[1] + off * h.out_stride[1], io.out1, m * h.out_stride[1], cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h.out[2] + off, io.st, m, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(e->io_done[k], st));
     }
     CK(cudaStreamSynchronize(e->stream[0]));
     CK(cudaStreamSynchronize(e->stream[1]));

@@ -28,7 +28,9 @@ ACT_FN ge ge_neg(const ge& p) { ge r; r.X = fe_neg(p.X); r.Y = p.Y; r.Z = p.Z; r
 // ptxas marshals call arguments and results with IMAD.MOV, which runs on the integer-multiply pipe -- the pipe this
 // code is bound by.  An exclusive-or with a run-time zero that ptxas cannot fold is a copy that is guaranteed to run on the
 // ALU pipe (LOP3; an add would become IMAD.IADD), and the register allocator can then place its result directly in the argument registers.
-// ACT_ALU_COPY bit 0: copy arguments, bit 1: copy results.
+// ACT_ALU_COPY bit 0: copy arguments, bit 1: copy results.  (Round 1i repeated the experiment with hand-placed one-for-one
+// copies -- 0 IMAD.MOV left in the doubling, same instruction count: no change in time, profiles/r01i_variants_alu_copy_targeted.txt:
+// the kernel is bound by instructions issued, not by the multiply pipe's cycles.)
 #ifndef ACT_ALU_COPY
 #define ACT_ALU_COPY 0
 #endif
@@ -76,10 +78,11 @@ ACT_GE_FN ge ge_add_cached(ge p, ge_cached q) {
     u32 zc_ = act_zero(); (void)zc_;
     fe PP = GE_MUL(fe_add(p.Y, p.X), q.YpX);
     fe MM = GE_MUL(fe_sub(p.Y, p.X), q.YmX);
+    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
     fe TT = GE_MUL(p.T, q.T2d);
     fe ZZ = GE_MUL(p.Z, q.Z);
     fe ZZ2 = fe_add(ZZ, ZZ);
-    fe E = fe_sub(PP, MM), H = fe_add(PP, MM), G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
+    fe G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
     ge r;
     r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
     return r;
@@ -89,9 +92,10 @@ ACT_GE_FN ge ge_add_niels(ge p, ge_niels q) {
     u32 zc_ = act_zero(); (void)zc_;
     fe PP = GE_MUL(fe_add(p.Y, p.X), q.ypx);
     fe MM = GE_MUL(fe_sub(p.Y, p.X), q.ymx);
+    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
     fe TT = GE_MUL(p.T, q.xy2d);
     fe ZZ2 = fe_add(p.Z, p.Z);
-    fe E = fe_sub(PP, MM), H = fe_add(PP, MM), G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
+    fe G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
     ge r;
     r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
     return r;
@@ -131,11 +135,13 @@ ACT_FN ge ge_dbl(const ge& p, bool want_t) { return want_t ? ge_dbl_t(p) : ge_db
 // B200: the 17-37 KB loop bodies miss the instruction cache and run 7-25 % slower than the call form, see DESIGN.md.)
 ACT_FN ge ge_dbl_u(const ge& p, bool want_t) {
     u32 zc_ = act_zero(); (void)zc_;
-    fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y), ZZ = GE_SQ(p.Z);
-    fe ZZ2 = fe_add(ZZ, ZZ);
-    fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
+    fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y);
     fe Yc = fe_add(YY, XX), Zc = fe_sub(YY, XX);
-    fe Xc = fe_sub(XpY2, Yc), Tc = fe_sub(ZZ2, Zc);
+    fe ZZ = GE_SQ(p.Z);
+    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe Tc = fe_sub(ZZ2, Zc);
+    fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
+    fe Xc = fe_sub(XpY2, Yc);
     ge r;
     r.X = GE_MUL(Xc, Tc); r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Zc, Tc);
     r.T = p.T;
