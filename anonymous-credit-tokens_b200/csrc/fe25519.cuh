@@ -175,6 +175,20 @@ ACT_FN void fe_row_chain(u32* acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 bi) {
         : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bi));
 }
+// the same row into words that include a still-zero last word: hi(a*b) + 0 + carry <= 2^32 - 1, the chain cannot carry out
+// and the capture is dropped (which rows qualify: tools/check_fe_rows.py, checked there on extreme operands)
+ACT_FN void fe_row_chain_fresh(u32* acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bi));
+}
 #endif
 
 // t[0..8] (value < 39 * 2^256) -> loosely reduced fe
@@ -252,11 +266,13 @@ ACT_FN fe fe_mul_inl(const fe& a, const fe& b) {
 #if ACT_PTX
     u32 ev[18], od[18];
     ACT_UNROLL for (int i = 0; i < 18; i++) { ev[i] = 0; od[i] = 0; }
+    // 16 rows; the first row to reach a new last word needs no carry capture (7 captures instead of 16)
     ACT_UNROLL for (int i = 0; i < 8; i += 2) {
-        fe_row_chain(ev + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
-        fe_row_chain(od + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+        if (i == 0) fe_row_chain_fresh(ev + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+        else fe_row_chain(ev + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+        fe_row_chain_fresh(od + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
         fe_row_chain(od + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
-        fe_row_chain(ev + i + 2, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+        fe_row_chain_fresh(ev + i + 2, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
     }
     // r = ev + (od << 32), one 15-word carry chain in a single asm statement (30 operands)
     ACT_UNROLL for (int i = 0; i < 16; i++) r[i] = ev[i];
@@ -293,29 +309,27 @@ ACT_FN fe fe_mul_inl(const fe& a, const fe& b) {
 #if ACT_PTX
 // ---- GENERATED by tools/gen_fe_sq.py (layout verified there against big-int squaring) ----
 // 28 off-diagonal products in even/odd carry chains, doubled, plus the 8 diagonal squares: 36 wide
-// multiply-adds instead of 64.
+// multiply-adds instead of 64.  A chain ends with a carry capture only where its last word may already be non-zero.
 ACT_FN void fe_sq_wide(u32* r, const fe& a) {
     u32 ev[16], od[16];
     ACT_UNROLL for (int i = 0; i < 16; i++) { ev[i] = 0; od[i] = 0; }
-    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
-        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
-        "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
-        "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
-        "madc.lo.cc.u32 %4, %9, %12, %4;\n\t"
-        "madc.hi.cc.u32 %5, %9, %12, %5;\n\t"
-        "madc.lo.cc.u32 %6, %9, %13, %6;\n\t"
-        "madc.hi.cc.u32 %7, %9, %13, %7;\n\t"
-        "addc.u32 %8, %8, 0;"
-        : "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8])
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %8, %11, %4;\n\t"
+        "madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+        "madc.lo.cc.u32 %6, %8, %12, %6;\n\t"
+        "madc.hi.u32 %7, %8, %12, %7;"
+        : "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7])
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]));
-    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
-        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
-        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
-        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
-        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
-        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
-        "addc.u32 %6, %6, 0;"
-        : "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]), "+r"(ev[8])
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
+        "madc.lo.cc.u32 %4, %6, %9, %4;\n\t"
+        "madc.hi.u32 %5, %6, %9, %5;"
+        : "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7])
         : "r"(a.v[0]), "r"(a.v[2]), "r"(a.v[4]), "r"(a.v[6]));
     asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
         "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
@@ -326,23 +340,21 @@ ACT_FN void fe_sq_wide(u32* r, const fe& a) {
         "addc.u32 %6, %6, 0;"
         : "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8])
         : "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[4]), "r"(a.v[6]));
-    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
-        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
-        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
-        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
-        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
-        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
-        "addc.u32 %6, %6, 0;"
-        : "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]), "+r"(ev[8]), "+r"(ev[9]), "+r"(ev[10])
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
+        "madc.lo.cc.u32 %4, %6, %9, %4;\n\t"
+        "madc.hi.u32 %5, %6, %9, %5;"
+        : "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7]), "+r"(ev[8]), "+r"(ev[9])
         : "r"(a.v[1]), "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]));
-    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
-        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
-        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
-        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
-        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
-        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
-        "addc.u32 %6, %6, 0;"
-        : "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "+r"(od[9]), "+r"(od[10])
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
+        "madc.lo.cc.u32 %4, %6, %9, %4;\n\t"
+        "madc.hi.u32 %5, %6, %9, %5;"
+        : "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "+r"(od[9])
         : "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]));
     asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
         "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
@@ -358,19 +370,17 @@ ACT_FN void fe_sq_wide(u32* r, const fe& a) {
         "addc.u32 %4, %4, 0;"
         : "+r"(od[6]), "+r"(od[7]), "+r"(od[8]), "+r"(od[9]), "+r"(od[10])
         : "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[6]));
-    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
-        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
-        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
-        "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
-        "addc.u32 %4, %4, 0;"
-        : "+r"(ev[8]), "+r"(ev[9]), "+r"(ev[10]), "+r"(ev[11]), "+r"(ev[12])
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "madc.lo.cc.u32 %2, %4, %6, %2;\n\t"
+        "madc.hi.u32 %3, %4, %6, %3;"
+        : "+r"(ev[8]), "+r"(ev[9]), "+r"(ev[10]), "+r"(ev[11])
         : "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]));
-    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
-        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
-        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
-        "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
-        "addc.u32 %4, %4, 0;"
-        : "+r"(od[8]), "+r"(od[9]), "+r"(od[10]), "+r"(od[11]), "+r"(od[12])
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "madc.lo.cc.u32 %2, %4, %6, %2;\n\t"
+        "madc.hi.u32 %3, %4, %6, %3;"
+        : "+r"(od[8]), "+r"(od[9]), "+r"(od[10]), "+r"(od[11])
         : "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[7]));
     asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
         "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
@@ -382,15 +392,13 @@ ACT_FN void fe_sq_wide(u32* r, const fe& a) {
         "addc.u32 %2, %2, 0;"
         : "+r"(od[10]), "+r"(od[11]), "+r"(od[12])
         : "r"(a.v[5]), "r"(a.v[6]));
-    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-        "addc.u32 %2, %2, 0;"
-        : "+r"(ev[12]), "+r"(ev[13]), "+r"(ev[14])
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, %1;"
+        : "+r"(ev[12]), "+r"(ev[13])
         : "r"(a.v[5]), "r"(a.v[7]));
-    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-        "addc.u32 %2, %2, 0;"
-        : "+r"(od[12]), "+r"(od[13]), "+r"(od[14])
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, %1;"
+        : "+r"(od[12]), "+r"(od[13])
         : "r"(a.v[6]), "r"(a.v[7]));
     ACT_UNROLL for (int i = 0; i < 16; i++) r[i] = ev[i];
     asm("add.cc.u32 %0, %0, %15;\n\t"

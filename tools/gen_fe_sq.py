@@ -23,9 +23,25 @@ def chains():
     return out
 
 
+def capture_flags():
+    """A chain needs its final `addc top, top, 0` only if its last word may be non-zero before the chain runs: into a word
+    that is still zero, hi(a*b) + carry <= 2^32 - 1 cannot carry out (tools/check_fe_rows.py checks this exhaustively on
+    extreme operands)."""
+    written = {"ev": set(), "od": set()}
+    flags = []
+    for acc, start, prods in chains():
+        top = start + 2 * len(prods) - 1
+        need = top in written[acc]
+        flags.append(need)
+        written[acc].update(range(start, top + 1))
+        if need:
+            written[acc].add(top + 1)
+    return flags
+
+
 def emulate(a):
     ev = [0] * 18; od = [0] * 18
-    for acc_name, start, prods in chains():
+    for (acc_name, start, prods), need in zip(chains(), capture_flags()):
         acc = ev if acc_name == "ev" else od
         carry = 0
         w = start
@@ -34,8 +50,11 @@ def emulate(a):
             t = acc[w] + (p & M32) + carry; acc[w] = t & M32; carry = t >> 32
             t = acc[w + 1] + (p >> 32) + carry; acc[w + 1] = t & M32; carry = t >> 32
             w += 2
-        t = acc[w] + carry; acc[w] = t & M32
-        assert t >> 32 == 0
+        if need:
+            t = acc[w] + carry; acc[w] = t & M32
+            assert t >> 32 == 0
+        else:
+            assert carry == 0
     # r = ev + (od << 32)
     r = [0] * 16
     r[0] = ev[0]; carry = 0
@@ -77,9 +96,9 @@ def emit():
     L.append("ACT_FN void fe_sq_wide(u32* r, const fe& a) {")
     L.append("    u32 ev[16], od[16];")
     L.append("    ACT_UNROLL for (int i = 0; i < 16; i++) { ev[i] = 0; od[i] = 0; }")
-    for acc, start, prods in chains():
+    for (acc, start, prods), need in zip(chains(), capture_flags()):
         n = len(prods)
-        words = list(range(start, start + 2 * n + 1))
+        words = list(range(start, start + 2 * n + (1 if need else 0)))
         ops = []
         # operand numbering: outputs first (2n+1), then a-limb inputs
         limbs = []
@@ -94,8 +113,10 @@ def emit():
         for k, (i, j) in enumerate(prods):
             lo = "mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32"
             lines.append('%s %%%d, %s, %s, %%%d;' % (lo, 2 * k, opn(i), opn(j), 2 * k))
-            lines.append('madc.hi.cc.u32 %%%d, %s, %s, %%%d;' % (2 * k + 1, opn(i), opn(j), 2 * k + 1))
-        lines.append('addc.u32 %%%d, %%%d, 0;' % (2 * n, 2 * n))
+            hi = "madc.hi.cc.u32" if (need or k < n - 1) else "madc.hi.u32"
+            lines.append('%s %%%d, %s, %s, %%%d;' % (hi, 2 * k + 1, opn(i), opn(j), 2 * k + 1))
+        if need:
+            lines.append('addc.u32 %%%d, %%%d, 0;' % (2 * n, 2 * n))
         body = '\\n\\t"\n        "'.join(lines)
         outs = ", ".join('"+r"(%s[%d])' % (acc, w) for w in words)
         ins = ", ".join('"r"(a.v[%d])' % x for x in limbs)
