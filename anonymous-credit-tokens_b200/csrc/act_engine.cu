@@ -21,27 +21,37 @@
 // ---------------------------------------------------------------------------------------------------
 // kernels: thin index wrappers around the per-thread bodies in act_device.cuh
 // ---------------------------------------------------------------------------------------------------
+// threads per block of the thread-per-request kernels; 512 threads (16 warps, 128 registers each) resident per SM
+#ifndef ACT_ISSUE_BLOCK
 #define ACT_ISSUE_BLOCK 128
+#endif
+#ifndef ACT_HEAD_BLOCK
 #define ACT_HEAD_BLOCK 64
+#endif
+#ifndef ACT_SIGN_BLOCK
 #define ACT_SIGN_BLOCK 64
+#endif
 #define ACT_HASH_BLOCK 128
+#define ACT_ISSUE_BPS (512 / ACT_ISSUE_BLOCK)
+#define ACT_HEAD_BPS (512 / ACT_HEAD_BLOCK)
+#define ACT_SIGN_BPS (512 / ACT_SIGN_BLOCK)
 
-__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issue_kernel(const act_ctx* C, size_t n, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status) {
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, ACT_ISSUE_BPS) issue_kernel(const act_ctx* C, size_t n, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issue_thread(C, i, req, cs, rnd, resp, status);
 }
 // the two halves of issue for the sequential-RNG contract (act_batch_issue_seq)
-__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issue_mode_kernel(const act_ctx* C, size_t n, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status,
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, ACT_ISSUE_BPS) issue_mode_kernel(const act_ctx* C, size_t n, const u32* req, const u32* cs, const u32* rnd, u32* resp, u8* status,
                                                                        int mode, const u32* rnd_index) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issue_thread(C, i, req, cs, rnd, resp, status, mode, rnd_index);
 }
-__global__ void __launch_bounds__(ACT_SIGN_BLOCK, 8) refund_sign_seq_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* rnd, const u32* kprime, const u8* status,
+__global__ void __launch_bounds__(ACT_SIGN_BLOCK, ACT_SIGN_BPS) refund_sign_seq_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* rnd, const u32* kprime, const u8* status,
                                                                            u32* refunds, u32* nullifiers, const u32* rnd_index, const u32* kwords) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) refund_sign_thread(C, p, proofs, rnd, kprime, status, refunds, nullifiers, rnd_index, kwords);
 }
-__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) issuance_check_kernel(const act_ctx* C, size_t n, const u32* K, const u32* resp, u8* status) {
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, ACT_ISSUE_BPS) issuance_check_kernel(const act_ctx* C, size_t n, const u32* K, const u32* resp, u8* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issuance_check_thread(C, i, K, resp, status);
 }
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(ACT_ENC_BLOCK, 4) spend_encode_kernel(const ac
 __global__ void __launch_bounds__(ACT_L, 4) prove_range_kernel(const act_ctx* C, prove_rng R, size_t m, const u32* tokens, const u32* charges, u32* cpts) {
     for (size_t p = blockIdx.x; p < m; p += gridDim.x) prove_range_thread(C, &R, p, p, threadIdx.x, tokens, charges, cpts);
 }
-__global__ void __launch_bounds__(ACT_HEAD_BLOCK, 8) prove_head_kernel(const act_ctx* C, prove_rng R, size_t m, const u32* tokens, u32* items, u32* aux, u8* status) {
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK, ACT_HEAD_BPS) prove_head_kernel(const act_ctx* C, prove_rng R, size_t m, const u32* tokens, u32* items, u32* aux, u8* status) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < m) prove_head_thread(C, &R, p, p, tokens, items, aux, status);
 }
@@ -142,11 +152,11 @@ __global__ void __launch_bounds__(ACT_L, 4) prove_finish_kernel(const act_ctx* C
                                                                const u32* aux, const u32* gammas, const u8* status, u32* proofs, u32* prerefunds) {
     for (size_t p = blockIdx.x; p < m; p += gridDim.x) prove_finish_thread(C, &R, p, p, threadIdx.x, tokens, charges, items, aux, gammas, status, proofs, prerefunds);
 }
-__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, 4) request_kernel(const act_ctx* C, size_t n, const u32* pre, const u32* rnd, u32* req) {
+__global__ void __launch_bounds__(ACT_ISSUE_BLOCK, ACT_ISSUE_BPS) request_kernel(const act_ctx* C, size_t n, const u32* pre, const u32* rnd, u32* req) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) request_thread(C, i, pre, rnd, req);
 }
-__global__ void __launch_bounds__(ACT_HEAD_BLOCK, 8) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK, ACT_HEAD_BPS) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) spend_head_thread(C, p, proofs, items, com_niels, kprime, flags);
 }
@@ -158,11 +168,11 @@ __global__ void __launch_bounds__(ACT_HASH_BLOCK) spend_finish_kernel(const act_
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) spend_finish_thread(C, p, proofs, cvs, flags, status);
 }
-__global__ void __launch_bounds__(ACT_SIGN_BLOCK, 8) refund_sign_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* rnd, const u32* kprime, const u8* status, u32* refunds, u32* nullifiers) {
+__global__ void __launch_bounds__(ACT_SIGN_BLOCK, ACT_SIGN_BPS) refund_sign_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* rnd, const u32* kprime, const u8* status, u32* refunds, u32* nullifiers) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) refund_sign_thread(C, p, proofs, rnd, kprime, status, refunds, nullifiers);
 }
-__global__ void __launch_bounds__(ACT_HEAD_BLOCK, 8) refund_check_kernel(const act_ctx* C, size_t n, const u32* com, const u32* refund, u8* status) {
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK, ACT_HEAD_BPS) refund_check_kernel(const act_ctx* C, size_t n, const u32* com, const u32* refund, u8* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) refund_check_thread(C, i, com, refund, status);
 }

@@ -10,14 +10,16 @@ KINDS = ["range", "head", "hash", "finish", "sign", "issue", "icheck", "rcheck",
 
 def fixtures(u=256):
     import corpus
-    path = "/tmp/variant_fixtures.npz"
+    path = "/tmp/variant_fixtures2.npz"
     ctx = corpus.make_ctx(corpus.BENCH_PARAMS)
     if os.path.exists(path):
         d = np.load(path)
         return ctx, {k: d[k] for k in d.files}
     base = corpus.gen_valid(ctx, u, seed=b"variant-bench", threads=os.cpu_count())
     o_ref, o_nul, o_st, _ = ctx.batch_refund(base["proofs"], base["rnd"], threads=os.cpu_count())
-    d = {"proofs": base["proofs"], "rnd": base["rnd"], "o_ref": o_ref, "o_nul": o_nul, "o_st": o_st}
+    o_resp, o_ist, _ = ctx.batch_issue(base["req"], base["cs"], base["rnd"])
+    d = {"proofs": base["proofs"], "rnd": base["rnd"], "o_ref": o_ref, "o_nul": o_nul, "o_st": o_st,
+         "req": base["req"], "cs": base["cs"], "o_resp": o_resp, "o_ist": o_ist}
     np.savez(path, **d)
     return ctx, d
 
@@ -48,7 +50,18 @@ def child(n, name):
     lib.act_engine_get_timing(eng._h, ms, cnt)
     k = {KINDS[i]: round(ms[i] / reps, 3) for i in range(9) if cnt[i]}
     tot = sum(k.values())
-    print(json.dumps({"variant": name, "n": n, "ok": ok, "kernel_ms": k, "sum_ms": round(tot, 2), "proofs_per_s_kernels": round(n / tot * 1e3), "range_proofs_per_s": round(n / k["range"] * 1e3), "wall_e2e_proofs_per_s": round(n / wall)}), flush=True)
+    # batch_issue of 16 n requests (tiled), device time of the issue kernel
+    ni = 16 * n
+    req = np.tile(d["req"].reshape(u, -1), (ni // u, 1)).reshape(-1).copy(); cs = np.tile(d["cs"].reshape(u, -1), (ni // u, 1)).reshape(-1).copy()
+    irnd = np.tile(d["rnd"].reshape(u, -1), (ni // u, 1)).reshape(-1).copy()
+    resp, ist = eng.batch_issue(req, cs, irnd)
+    ok = ok and bool((ist == 0).all() and (resp.reshape(ni // u, -1) == d["o_resp"].reshape(1, -1)).all())
+    lib.act_engine_get_timing(eng._h, ms, cnt)
+    for _ in range(reps):
+        eng.batch_issue(req, cs, irnd)
+    lib.act_engine_get_timing(eng._h, ms, cnt)
+    k["issue"] = round(ms[5] / reps, 3)
+    print(json.dumps({"variant": name, "n": n, "ok": ok, "issues_per_s": round(ni / k["issue"] * 1e3), "kernel_ms": k, "sum_ms": round(tot, 2), "proofs_per_s_kernels": round(n / tot * 1e3), "range_proofs_per_s": round(n / k["range"] * 1e3), "wall_e2e_proofs_per_s": round(n / wall)}), flush=True)
 
 
 if __name__ == "__main__":
