@@ -648,15 +648,21 @@ ACT_FN void spend_head_thread(const act_ctx* C, size_t p, const u32* proofs, u32
     sc k_bar = load_scalar(pf + 8 * 524), s_bar = load_scalar(pf + 8 * 525);
     store_scalar(it, k);               // transcript.add_scalar(&k): reduced bytes          (:832)
     store8(it + 8, aw); store8(it + 16, bw);
-    vb_table t[3];
+    vb_table t[2];
     {
-        ge Abar;
-        vb_mul_ct_(&Abar, &Ap, &C->x);                                                     // (:791) secret x
-        // A1 = A'*e_bar + B*r2_bar - Abar*gamma                                           (:793-795)
-        vb_table_build(&t[0], Ap); vb_table_build(&t[1], Bb); vb_table_build(&t[2], Abar);
-        sc ss[3] = {e_bar, r2_bar, gamma};
-        bool ng[3] = {false, false, true};
-        ge A1 = vb_mul_multi<3>(t, ss, ng);
+        // A1 = A'*e_bar + B*r2_bar - Abar*gamma with Abar = A'*x                          (:791,793-795)
+        //    = A'*(e_bar - x*gamma) + B*r2_bar: Abar is never formed (it is not hashed); the scalar on A' depends on the
+        //    secret x, so that term scans its table in full, the B term (public scalar) indexes directly.  One doubling chain.
+        vb_table_build(&t[0], Ap); vb_table_build(&t[1], Bb);
+        sc sa = sc_bias<4>(sc_sub(e_bar, sc_mul(C->x, gamma))), sb = sc_bias<4>(r2_bar);
+        ge A1 = ge_identity();
+        ACT_NOUNROLL for (int i = 63; i >= 0; i--) {
+            if (i != 63) {
+                A1 = ge_dbl(A1, false); A1 = ge_dbl(A1, false); A1 = ge_dbl(A1, false); A1 = ge_dbl(A1, true);
+            }
+            A1 = ge_add_cached(A1, vb_lookup_ct(&t[0], sc_digit<4>(sa, i)));
+            A1 = ge_add_cached(A1, vb_lookup(&t[1], sc_digit<4>(sb, i), false));
+        }
         store_point(it + 24, A1);
     }
     {
