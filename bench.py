@@ -37,10 +37,10 @@ UNIT = "proofs/s"
 # the algorithm this engine implements (DESIGN.md section 4 has the breakdown; SURVEY.md 8d estimated 4.8e7 / 7.0e5 for
 # a wNAF formulation -- the implemented shared-chain / wide-window / batched-encode algorithm needs less):
 #   range kernel per com_j: 1506 S + 2615 M = 2.545e5  -> x128 = 3.26e7 per proof
-#   encode 7.1e5, head 9.9e5, sign 4.6e5 per proof
+#   encode 7.1e5, head 8.0e5 (A1 as a two-term sum, A-bar never formed), sign 3.9e5 (A and Y_A share a doubling chain) per proof
 LIMB_MACS_PER_SPEND_RANGE = 3.26e7
-LIMB_MACS_PER_SPEND = 3.26e7 + 7.1e5 + 9.9e5 + 4.6e5
-LIMB_MACS_PER_ISSUE = 6.7e5
+LIMB_MACS_PER_SPEND = 3.26e7 + 7.1e5 + 8.0e5 + 3.9e5
+LIMB_MACS_PER_ISSUE = 6.0e5
 # IMAD.WIDE.U32 issues at 32 lanes per clock per SM on sm_100 (ncu: 2 fma-heavy pipe cycles per warp instruction at
 # 0.5 instructions/clock/SMSP; profiles/r01d_*.txt) -> integer-multiply roofline = SMs x 32 x SM clock
 IMAD_WIDE_LANES_PER_CLK_PER_SM = 32

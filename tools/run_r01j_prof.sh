@@ -1,0 +1,8 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+make -C oracle -s > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:spend_range -s 1 -c 1 -o gpurun_out/range_r1j -f python tools/prof_spend.py 2368 2 > gpurun_out/prof_j.log 2>&1; tail -2 gpurun_out/prof_j.log
+timeout 600 ncu --set full --clock-control none -k regex:issue_kernel -c 1 -o gpurun_out/issue_r1j -f python tools/prof_spend.py 2368 1 > gpurun_out/prof_j3.log 2>&1; tail -2 gpurun_out/prof_j3.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01j_launches.csv python tools/prof_spend.py 16384 1 > gpurun_out/prof_j2.log 2>&1
+ls -la gpurun_out/*.ncu-rep
