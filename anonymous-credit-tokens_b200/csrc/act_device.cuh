@@ -78,9 +78,11 @@ ACT_HD u32 fb_parts_of(u32 bits) { u32 n = fb_ent_of(bits) - 1; return n >= ACT_
 #define ACT_BASE_H1 1
 #define ACT_BASE_H2 2
 #define ACT_BASE_H3 3
+#define ACT_BASE_W 4     // the issuer's public key: fixed per engine, so the client-side checks use a table for it too
+#define ACT_FB_BASES 5
 
 struct act_ctx {
-    fb_tab fb[4];            // vartime fixed-base tables for G, H1, H2, H3 (global memory, L2 resident)
+    fb_tab fb[ACT_FB_BASES]; // vartime fixed-base tables for G, H1, H2, H3, W (global memory, L2 resident)
     const ge_niels* ct_g;    // constant-time table for G
     sc x;                    // issuer secret
     ge W;                    // issuer public key
@@ -514,9 +516,10 @@ ACT_NOINLINE u32 dleq_check_(const act_ctx* C, int kind, const sc* c, const sc* 
     sc ss[2] = {*z, *gamma};
     bool ng[2] = {false, true};
     ge Y_A = vb_mul_multi<2>(t, ss, ng);
-    vb_table_build(&t[0], X_G);
-    ge Y_G = vb_mul(&t[0], *gamma, true);
-    Y_G = fb_accumulate(Y_G, C->fb[ACT_BASE_G], *z, false);
+    // Y_G = G*z - X_G*gamma with X_G = G*e + W  =  G*(z - e*gamma) - W*gamma: both bases are fixed per engine, so the
+    // variable-base multiplication of the reference's formula becomes two table walks
+    ge Y_G = fb_accumulate(ge_identity(), C->fb[ACT_BASE_G], sc_sub(*z, sc_mul(*e, *gamma)), false);
+    Y_G = fb_accumulate(Y_G, C->fb[ACT_BASE_W], *gamma, true);
     tr_small tr;
     u32 w[8];
     tr_init(&tr, C, kind);

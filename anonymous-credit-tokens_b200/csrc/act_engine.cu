@@ -181,21 +181,21 @@ __global__ void __launch_bounds__(ACT_HEAD_BLOCK, ACT_HEAD_BPS) refund_check_ker
 __global__ void params_derive_kernel(const u8* dom, u32 dlen, u32* out) {
     if (blockIdx.x == 0 && threadIdx.x == 0) params_derive_thread(dom, dlen, out);
 }
-// decodes H1,H2,H3,W into bases[1..3], W; bases[0] = G.  ok[0] = all valid
-__global__ void setup_decode_kernel(const u32* enc /* 4 x 8 words: H1,H2,H3,W */, ge* bases /* 4 */, ge* W, u32* ok) {
+// decodes H1,H2,H3,W into bases[1..4] (and W); bases[0] = G.  ok[0] = all valid
+__global__ void setup_decode_kernel(const u32* enc /* 4 x 8 words: H1,H2,H3,W */, ge* bases /* ACT_FB_BASES */, ge* W, u32* ok) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         u32 v = 1;
         bases[0] = ge_basepoint();
-        for (int i = 0; i < 3; i++) v &= ristretto_decode_(&bases[1 + i], enc + 8 * i);
-        v &= ristretto_decode_(W, enc + 24);
+        for (int i = 0; i < 4; i++) v &= ristretto_decode_(&bases[1 + i], enc + 8 * i);
+        *W = bases[ACT_BASE_W];
         *ok = v;
     }
 }
 // the wide-window tables of G, H1, H2, H3: one thread per (base, window, part)
-struct fb_layout { u32 bits[4]; u32 first_thread[5]; size_t offset[4]; };
+struct fb_layout { u32 bits[ACT_FB_BASES]; u32 first_thread[ACT_FB_BASES + 1]; size_t offset[ACT_FB_BASES]; };
 __global__ void build_fb_tables_kernel(const ge* bases, ge_niels* tabs, fb_layout L) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L.first_thread[4]) return;
+    if (t >= L.first_thread[ACT_FB_BASES]) return;
     int base = 0;
     while (t >= L.first_thread[base + 1]) base++;
     u32 r = t - L.first_thread[base], parts = fb_parts_of(L.bits[base]);
@@ -203,13 +203,13 @@ __global__ void build_fb_tables_kernel(const ge* bases, ge_niels* tabs, fb_layou
 }
 static fb_layout make_fb_layout(size_t* total_entries) {
     fb_layout L;
-    const u32 bits[4] = {ACT_FB_BITS, ACT_FB_BITS_HOT, ACT_FB_BITS, ACT_FB_BITS_HOT};   // G, H1, H2, H3
+    const u32 bits[ACT_FB_BASES] = {ACT_FB_BITS, ACT_FB_BITS_HOT, ACT_FB_BITS, ACT_FB_BITS_HOT, ACT_FB_BITS};   // G, H1, H2, H3, W
     size_t off = 0; u32 th = 0;
-    for (int b = 0; b < 4; b++) {
+    for (int b = 0; b < ACT_FB_BASES; b++) {
         L.bits[b] = bits[b]; L.offset[b] = off; L.first_thread[b] = th;
         off += fb_size_of(bits[b]); th += fb_win_of(bits[b]) * fb_parts_of(bits[b]);
     }
-    L.first_thread[4] = th;
+    L.first_thread[ACT_FB_BASES] = th;
     *total_entries = off;
     return L;
 }
@@ -491,14 +491,14 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         size_t fb_entries = 0;
         fb_layout L = make_fb_layout(&fb_entries);
         CKB(cudaMalloc((void**)&e->d_tables, sizeof(ge_niels) * (fb_entries + ACT_CT_SIZE)));
-        CKB(cudaMalloc((void**)&e->d_bases, sizeof(ge) * 4));
+        CKB(cudaMalloc((void**)&e->d_bases, sizeof(ge) * ACT_FB_BASES));
         CKB(cudaMalloc((void**)&d_enc, 128));
         CKB(cudaMalloc((void**)&d_ok, 4));
         CKB(cudaMalloc((void**)&d_W, sizeof(ge)));
         CKB(cudaMemcpy(d_enc, h, 96, cudaMemcpyHostToDevice));
         CKB(cudaMemcpy(d_enc + 24, pk_w, 32, cudaMemcpyHostToDevice));
         setup_decode_kernel<<<1, 1>>>(d_enc, e->d_bases, d_W, d_ok);
-        build_fb_tables_kernel<<<(L.first_thread[4] + 31) / 32, 32>>>(e->d_bases, e->d_tables, L);
+        build_fb_tables_kernel<<<(L.first_thread[ACT_FB_BASES] + 31) / 32, 32>>>(e->d_bases, e->d_tables, L);
         build_ct_table_kernel<<<1, ACT_CT_WIN>>>(e->d_bases, e->d_tables + fb_entries);
         CKB(cudaGetLastError());
         u32 ok = 0;
@@ -507,7 +507,7 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         // context
         act_ctx hc;
         memset(&hc, 0, sizeof hc);
-        for (int b = 0; b < 4; b++) { hc.fb[b].p = e->d_tables + L.offset[b]; hc.fb[b].bits = L.bits[b]; hc.fb[b].win = fb_win_of(L.bits[b]); hc.fb[b].ent = fb_ent_of(L.bits[b]); }
+        for (int b = 0; b < ACT_FB_BASES; b++) { hc.fb[b].p = e->d_tables + L.offset[b]; hc.fb[b].bits = L.bits[b]; hc.fb[b].win = fb_win_of(L.bits[b]); hc.fb[b].ent = fb_ent_of(L.bits[b]); }
         hc.ct_g = e->d_tables + fb_entries;
         memcpy(hc.h_enc, h, 96);
         build_prefix(&hc, ACT_TR_REQUEST, "request", h);
@@ -539,7 +539,7 @@ extern "C" int act_public_key(int device, const uint8_t sk_x[32], uint8_t pk_w[3
     if (!sk_x || !pk_w) return fail_msg("act_public_key: null argument");
     CK(cudaSetDevice(device));
     ge* d_b = nullptr; ge_niels* d_t = nullptr; u32 *d_x = nullptr, *d_o = nullptr;
-    CK(cudaMalloc((void**)&d_b, sizeof(ge) * 4));
+    CK(cudaMalloc((void**)&d_b, sizeof(ge) * ACT_FB_BASES));
     CK(cudaMalloc((void**)&d_t, sizeof(ge_niels) * ACT_CT_SIZE));
     CK(cudaMalloc((void**)&d_x, 32)); CK(cudaMalloc((void**)&d_o, 32));
     ge hb[4];

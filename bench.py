@@ -376,6 +376,21 @@ def main():
     assert (o_ist == 0).all() and (d_resp[:8 * 160].cpu().numpy() == o_resp).all(), "issue output differs from oracle"
     issue_value = world * ni * K / (ims * 1e-3)
 
+    # ---- client-side checks (the verification halves of the two to_credit_token), device-resident:
+    # every response / refund just produced must verify ----
+    d_K = d_req.view(ni, 128)[:, :32].contiguous().view(-1)
+    d_cst = torch.full((ni,), 255, dtype=torch.uint8, device=dev)
+    icms = timed(lambda: eng.batch_issuance_check_dev(ni, d_K.data_ptr(), d_resp.data_ptr(), d_cst.data_ptr(), stream), 1, K)
+    assert (d_cst == 0).all(), "issuance_check rejected a response of batch_issue"
+    nrc = min(n, 131072)
+    d_com = d_proofs.view(n, PROOF_BYTES)[:nrc, 128:128 + 4096].contiguous().view(-1)
+    d_rst = torch.full((nrc,), 255, dtype=torch.uint8, device=dev)
+    rcms = timed(lambda: eng.batch_refund_check_dev(nrc, d_com.data_ptr(), d_ref.data_ptr(), d_rst.data_ptr(), stream), 1, K)
+    assert (d_rst == 0).all(), "refund_check rejected a refund of batch_verify_spend_and_refund"
+    client_checks = {"issuance_check": {"value": world * ni * K / (icms * 1e-3), "unit": "checks/s", "n": ni},
+                     "refund_check": {"value": world * nrc * K / (rcms * 1e-3), "unit": "checks/s", "n": nrc}}
+    del d_K, d_cst, d_com, d_rst
+
     # ---- mixed adversarial batch (BASELINE configs[4] shape): the same n proofs with a fraction tampered on the device, one
     # class per row of the mutation table, the expected status of every index known by construction;
     # then the engine's replay screen over the batch.  Timed like `value`; the un-tampered batch is restored afterwards. ----
@@ -477,6 +492,7 @@ def main():
                       "e2e": {"value": world * ni * Ke / e2e_issue_s, "h2d_bytes_per_step": world * ni * 288, "d2h_bytes_per_step": world * ni * 161},
                       "roofline_frac": LIMB_MACS_PER_ISSUE * issue_value / world / peak},
             "mixed_adversarial": mixed,
+            "client_checks": client_checks,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

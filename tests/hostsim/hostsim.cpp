@@ -40,25 +40,26 @@ static void build_prefix(act_ctx* c, int which, const char* label, const uint8_t
 EXPORT hs_ctx* hs_ctx_create(const uint8_t h[96], const uint8_t x[32], const uint8_t w[32]) {
     hs_ctx* H = new hs_ctx();
     memset(&H->c, 0, sizeof H->c);
-    ge bases[4];
+    ge bases[ACT_FB_BASES];
     bases[0] = ge_basepoint();
     u32 ok = 1, words[8];
     for (int i = 0; i < 3; i++) { memcpy(words, h + 32 * i, 32); ok &= ristretto_decode_(&bases[1 + i], words); }
     memcpy(words, w, 32);
     ok &= ristretto_decode_(&H->c.W, words);
     if (!ok) { delete H; return nullptr; }
+    bases[ACT_BASE_W] = H->c.W;
     // host build: every base at the narrow width (the wide 2^16 tables of the device build would take seconds to make on a CPU);
     // base 3 gets a different width than the others so that the per-table width logic is exercised
-    const u32 bits[4] = {ACT_FB_BITS, ACT_FB_BITS, ACT_FB_BITS, 11};
-    size_t off[5] = {0, 0, 0, 0, 0};
-    for (int b = 0; b < 4; b++) off[b + 1] = off[b] + fb_size_of(bits[b]);
-    H->tables.resize(off[4] + ACT_CT_SIZE);
-    for (int b = 0; b < 4; b++)
+    const u32 bits[ACT_FB_BASES] = {ACT_FB_BITS, ACT_FB_BITS, ACT_FB_BITS, 11, ACT_FB_BITS};
+    size_t off[ACT_FB_BASES + 1] = {0};
+    for (int b = 0; b < ACT_FB_BASES; b++) off[b + 1] = off[b] + fb_size_of(bits[b]);
+    H->tables.resize(off[ACT_FB_BASES] + ACT_CT_SIZE);
+    for (int b = 0; b < ACT_FB_BASES; b++)
         for (int win = 0; win < (int)fb_win_of(bits[b]); win++)
             for (int part = 0; part < (int)fb_parts_of(bits[b]); part++) build_fb_table_thread(&bases[b], bits[b], win, part, H->tables.data() + off[b]);
-    for (int win = 0; win < ACT_CT_WIN; win++) build_table_thread<4, ACT_CT_ENT>(&bases[0], win, H->tables.data() + off[4]);
-    for (int b = 0; b < 4; b++) { H->c.fb[b].p = H->tables.data() + off[b]; H->c.fb[b].bits = bits[b]; H->c.fb[b].win = fb_win_of(bits[b]); H->c.fb[b].ent = fb_ent_of(bits[b]); }
-    H->c.ct_g = H->tables.data() + off[4];
+    for (int win = 0; win < ACT_CT_WIN; win++) build_table_thread<4, ACT_CT_ENT>(&bases[0], win, H->tables.data() + off[ACT_FB_BASES]);
+    for (int b = 0; b < ACT_FB_BASES; b++) { H->c.fb[b].p = H->tables.data() + off[b]; H->c.fb[b].bits = bits[b]; H->c.fb[b].win = fb_win_of(bits[b]); H->c.fb[b].ent = fb_ent_of(bits[b]); }
+    H->c.ct_g = H->tables.data() + off[ACT_FB_BASES];
     memcpy(H->c.h_enc, h, 96);
     build_prefix(&H->c, ACT_TR_REQUEST, "request", h);
     build_prefix(&H->c, ACT_TR_RESPOND, "respond", h);
