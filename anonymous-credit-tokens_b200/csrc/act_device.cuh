@@ -185,8 +185,7 @@ ACT_FN ge fb_accumulate(ge acc, const fb_tab& T, const sc& s, bool negate) {
             const ge_niels* nxt = T.p + (size_t)(i + 1) * T.ent + (u32)(d < 0 ? -d : d);
             prefetch_line(nxt); prefetch_line(reinterpret_cast<const u8*>(nxt) + 95);
         }
-        ge_niels e = load_niels(cur);
-        acc = ge_add_niels(acc, ge_niels_cneg(e, neg));
+        acc = ge_add_niels_n(acc, load_niels(cur), neg);
     }
     return acc;
 }
@@ -308,7 +307,9 @@ ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
                 int dn = sc_digit<4>(b, (k + 1) * WIN + i);
                 prefetch_line(&t[k + 1].e[dn < 0 ? -dn : dn]);
             }
-            a = ge_add_cached(a, vb_lookup(&t[k], sc_digit<4>(b, k * WIN + i), true));
+            // the doubling that follows the last addition of a window does not read T (the very last window's does: T goes on)
+            int dk = sc_digit<4>(b, k * WIN + i);
+            a = ge_add_cached_u(a, tab_load(&t[k], (u32)(dk < 0 ? -dk : dk)), dk < 0 ? 0u : 1u, k + 1 < M || i == 0);   // -|d| * sign
         }
     }
     return a;
@@ -342,7 +343,7 @@ ACT_NOINLINE void vb_mul2_ct_(ge* out1, ge* out2, const ge* P, const sc* s1, con
             if (i != WIN - 1) {
                 ACT_NOUNROLL for (int d = 0; d < 4; d++) a = ge_dbl_u(a, d == 3);
             }
-            ACT_NOUNROLL for (int k = 0; k < M; k++) a = ge_add_cached(a, vb_lookup_ct(&t[k], sc_digit<4>(b, k * WIN + i)));
+            ACT_NOUNROLL for (int k = 0; k < M; k++) a = ge_add_cached_u(a, vb_lookup_ct(&t[k], sc_digit<4>(b, k * WIN + i)), 0u, k + 1 < M || i == 0);
         }
         if (w) *out2 = a; else *out1 = a;
     }

@@ -87,6 +87,25 @@ ACT_GE_FN ge ge_add_cached(ge p, ge_cached q) {
     r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
     return r;
 }
+// the addition of the window loops: r = p + (neg ? -q : q) with a run-time (warp-uniform) choice of producing T -- a doubling
+// (which does not read T) follows the last addition of every window: 7M instead of 8M there.  The negation of q is folded
+// in: -q swaps q's Y+X / Y-X and flips the sign of the T term, which swaps G and F (no field negation needed).
+ACT_FN ge ge_add_cached_u(const ge& p, const ge_cached& q, u32 neg, bool want_t) {
+    u32 zc_ = act_zero(); (void)zc_;
+    fe PP = GE_MUL(fe_add(p.Y, p.X), fe_select(q.YpX, q.YmX, neg));
+    fe MM = GE_MUL(fe_sub(p.Y, p.X), fe_select(q.YmX, q.YpX, neg));
+    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
+    fe TT = GE_MUL(p.T, q.T2d);
+    fe ZZ = GE_MUL(p.Z, q.Z);
+    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe G0 = fe_add(ZZ2, TT), F0 = fe_sub(ZZ2, TT);
+    fe G = fe_select(G0, F0, neg), F = fe_select(F0, G0, neg);
+    ge r;
+    r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F);
+    r.T = p.T;
+    if (want_t) r.T = GE_MUL(E, H);
+    return r;
+}
 // r = p + q for affine-Niels q, 7M
 ACT_GE_FN ge ge_add_niels(ge p, ge_niels q) {
     u32 zc_ = act_zero(); (void)zc_;
@@ -96,6 +115,20 @@ ACT_GE_FN ge ge_add_niels(ge p, ge_niels q) {
     fe TT = GE_MUL(p.T, q.xy2d);
     fe ZZ2 = fe_add(p.Z, p.Z);
     fe G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
+    ge r;
+    r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
+    return r;
+}
+// r = p + (neg ? -q : q) for an affine-Niels table entry, the negation folded in as in ge_add_cached_u (public data)
+ACT_FN ge ge_add_niels_n(const ge& p, const ge_niels& q, u32 neg) {
+    u32 zc_ = act_zero(); (void)zc_;
+    fe PP = GE_MUL(fe_add(p.Y, p.X), fe_select(q.ypx, q.ymx, neg));
+    fe MM = GE_MUL(fe_sub(p.Y, p.X), fe_select(q.ymx, q.ypx, neg));
+    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
+    fe TT = GE_MUL(p.T, q.xy2d);
+    fe ZZ2 = fe_add(p.Z, p.Z);
+    fe G0 = fe_add(ZZ2, TT), F0 = fe_sub(ZZ2, TT);
+    fe G = fe_select(G0, F0, neg), F = fe_select(F0, G0, neg);
     ge r;
     r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
     return r;
