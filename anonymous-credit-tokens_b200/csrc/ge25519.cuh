@@ -92,16 +92,17 @@ ACT_GE_FN ge ge_add_cached(ge p, ge_cached q) {
 // in: -q swaps q's Y+X / Y-X and flips the sign of the T term, which swaps G and F (no field negation needed).
 ACT_FN ge ge_add_cached_u(const ge& p, const ge_cached& q, u32 neg, bool want_t) {
     u32 zc_ = act_zero(); (void)zc_;
-    fe PP = GE_MUL(fe_add(p.Y, p.X), fe_select(q.YpX, q.YmX, neg));
-    fe MM = GE_MUL(fe_sub(p.Y, p.X), fe_select(q.YmX, q.YpX, neg));
-    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
+    // (statement and operand order chosen by the marshalling moves ptxas needs in the range kernel: 363 vs 381 instructions)
     fe TT = GE_MUL(p.T, q.T2d);
     fe ZZ = GE_MUL(p.Z, q.Z);
     fe ZZ2 = fe_add(ZZ, ZZ);
     fe G0 = fe_add(ZZ2, TT), F0 = fe_sub(ZZ2, TT);
+    fe PP = GE_MUL(fe_select(q.YpX, q.YmX, neg), fe_add(p.Y, p.X));
+    fe MM = GE_MUL(fe_select(q.YmX, q.YpX, neg), fe_sub(p.Y, p.X));
+    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
     fe G = fe_select(G0, F0, neg), F = fe_select(F0, G0, neg);
     ge r;
-    r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F);
+    r.X = GE_MUL(E, F); r.Z = GE_MUL(G, F); r.Y = GE_MUL(H, G);     // order chosen by the moves ptxas needs (369 vs 381 instructions)
     r.T = p.T;
     if (want_t) r.T = GE_MUL(E, H);
     return r;
@@ -176,7 +177,8 @@ ACT_FN ge ge_dbl_u(const ge& p, bool want_t) {
     fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
     fe Xc = fe_sub(XpY2, Yc);
     ge r;
-    r.X = GE_MUL(Xc, Tc); r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Zc, Tc);
+    // (call and operand order chosen by the marshalling moves ptxas needs for them in the range kernel: 262 vs 272 instructions)
+    r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Tc, Zc); r.X = GE_MUL(Tc, Xc);
     r.T = p.T;
     if (want_t) r.T = GE_MUL(Xc, Yc);
     return r;
