@@ -574,18 +574,20 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
     ACT_NOUNROLL for (int b = 0; b < 2; b++) {
         // b = 0: C'_j0 = [h2*w00 +] h3*z_j0 - com_j*gamma0_j                                 (:806-807,814-815)
         // b = 1: C'_j1 = [h2*w01 +] h3*z_j1 + h1*gamma01_j - com_j*gamma01_j                 (:808-809,816)
+        //        [..] for j = 0 only, added by spend_head_thread
         //        (the reference's base com_j - H1 is never formed: -(com_j - h1)*g = h1*g - com_j*g)
         // Scalars are re-derived from the proof bytes where they are used: nothing but the accumulator stays live.
         sc gb = load_scalar(pf + 8 * (140 + j));
         if (b) gb = sc_sub(load_scalar(pf + 8 * 132), gb);                                  // gamma01[j] (:801,811)
         gb = sc_half(gb);
         ge Q = vb_mul_split_neg<ACT_RANGE_SPLIT>(tabs, gb);
-        ACT_NOUNROLL for (int t = 0; t < 3; t++) {
+        // (the h2 terms exist for j = 0 only: one lane of one warp in four would run 40 additions alone, so stage 2 -- a thread
+        // per proof -- adds them to the stored halves instead, spend_head_thread)
+        ACT_NOUNROLL for (int t = 0; t < 2; t++) {
             int tab;
             sc s;
             if (t == 0) { tab = ACT_BASE_H3; s = load_scalar(pf + 8 * (268 + 2 * j + b)); }
-            else if (t == 1) { if (!b) continue; tab = ACT_BASE_H1; s = sc_sub(load_scalar(pf + 8 * 132), load_scalar(pf + 8 * (140 + j))); }
-            else { if (j != 0) continue; tab = ACT_BASE_H2; s = load_scalar(pf + 8 * (138 + b)); }
+            else { if (!b) continue; tab = ACT_BASE_H1; s = sc_sub(load_scalar(pf + 8 * 132), load_scalar(pf + 8 * (140 + j))); }
             Q = fb_accumulate(Q, C->fb[tab], sc_half(s), false);
         }
         store_fe(cp + 32 * b, Q.X); store_fe(cp + 32 * b + 8, Q.Y); store_fe(cp + 32 * b + 16, Q.Z); store_fe(cp + 32 * b + 24, Q.T);
@@ -633,11 +635,19 @@ ACT_FN void spend_encode_thread(const act_ctx* C, size_t p, int part, const u32*
 
 // =============================================================================================================
 // spend verification, stage 2: one thread per proof.  A-bar (secret x), A1, A2, K' (Horner), C
-// (src/lib.rs:787-799, 819-829).  Writes items 0..4 and 389, K' for the signing tail.
+// (src/lib.rs:787-799, 819-829).  Writes items 0..4 and 389, K' for the signing tail; completes C'_00, C'_01 in cpts.
 // =============================================================================================================
-ACT_FN void spend_head_thread(const act_ctx* C, size_t p, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
+ACT_FN void spend_head_thread(const act_ctx* C, size_t p, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags,
+                              u32* cpts /* halves of stage 1: the two of j = 0 get their h2 terms here, BEFORE the encode stage */) {
     const u32* pf = proofs + (size_t)ACT_PROOF_WORDS * p;
     u32* it = items + (size_t)ACT_ITEM_WORDS * p;
+    ACT_NOUNROLL for (int b = 0; b < 2; b++) {   // C'_00 += h2*w00, C'_01 += h2*w01 (as halves)            (:806,808)
+        u32* cp = cpts + ((size_t)2 * ACT_L * p + b) * 32;
+        ge Q;
+        load8_rw(Q.X.v, cp); load8_rw(Q.Y.v, cp + 8); load8_rw(Q.Z.v, cp + 16); load8_rw(Q.T.v, cp + 24);
+        Q = fb_accumulate(Q, C->fb[ACT_BASE_H2], sc_half(load_scalar(pf + 8 * (138 + b))), false);
+        store_fe(cp, Q.X); store_fe(cp + 8, Q.Y); store_fe(cp + 16, Q.Z); store_fe(cp + 24, Q.T);
+    }
     u32 aw[8], bw[8];
     load8(aw, pf + 16); load8(bw, pf + 24);
     ge Ap, Bb;

@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(ACT_ISSUE_BLOCK, ACT_ISSUE_BPS) request_kernel
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) request_thread(C, i, pre, rnd, req);
 }
-__global__ void __launch_bounds__(ACT_HEAD_BLOCK, ACT_HEAD_BPS) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags) {
+__global__ void __launch_bounds__(ACT_HEAD_BLOCK, ACT_HEAD_BPS) spend_head_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* items, const u32* com_niels, u32* kprime, u32* flags, u32* cpts) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n) spend_head_thread(C, p, proofs, items, com_niels, kprime, flags);
+    if (p < n) spend_head_thread(C, p, proofs, items, com_niels, kprime, flags, cpts);
 }
 __global__ void __launch_bounds__(ACT_HASH_BLOCK) spend_chunk_kernel(const act_ctx* C, size_t n, const u32* items, u32* cvs) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -694,9 +694,10 @@ static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, 
     size_t rblocks = (m * ACT_L + ACT_RANGE_BLOCK - 1) / ACT_RANGE_BLOCK;   // blocks that would hold one thread per com_j
     unsigned rgrid = rblocks < s->range_grid ? (unsigned)rblocks : s->range_grid;
     LAUNCH(e, K_RANGE, st, (spend_range_kernel<<<rgrid, ACT_RANGE_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, s->flags, s->tabs, s->cpts, s->counter)));
-    LAUNCH(e, K_ENCODE, st, (spend_encode_kernel<<<nblocks(m * ACT_ENC_PARTS, ACT_ENC_BLOCK), ACT_ENC_BLOCK, 0, st>>>(e->d_ctx, m, s->cpts, s->items, 2 * ACT_L, 133)));
+    // head before encode: it completes the two half-commitments of j = 0 (their h2 terms) that the encode stage then reads
     u32* kp = kprime_out ? kprime_out : s->kprime;
-    LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, kp, s->flags)));
+    LAUNCH(e, K_HEAD, st, (spend_head_kernel<<<nblocks(m, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->items, s->com_niels, kp, s->flags, s->cpts)));
+    LAUNCH(e, K_ENCODE, st, (spend_encode_kernel<<<nblocks(m * ACT_ENC_PARTS, ACT_ENC_BLOCK), ACT_ENC_BLOCK, 0, st>>>(e->d_ctx, m, s->cpts, s->items, 2 * ACT_L, 133)));
     LAUNCH(e, K_CHUNK, st, (spend_chunk_kernel<<<nblocks(m * ACT_SPEND_CHUNKS, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, s->items, s->cvs)));
     LAUNCH(e, K_FINISH, st, (spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status)));
     if (!kprime_out)

@@ -113,9 +113,9 @@ EXPORT void hs_refund(const hs_ctx* H, size_t n, const uint8_t* proofs, const ui
     std::vector<u32> cpts(n * 2 * ACT_L * 32 + 8);
     for (size_t p = 0; p < n; p++)
         for (int j = 0; j < ACT_L; j++) spend_range_thread(&H->c, p, j, pf.data(), items.data(), cn.data(), flags.data(), tabs.data(), cpts.data());
+    for (size_t p = 0; p < n; p++) spend_head_thread(&H->c, p, pf.data(), items.data(), cn.data(), kp.data(), flags.data(), cpts.data());
     for (size_t p = 0; p < n; p++)
         for (int part = 0; part < 2 * ACT_L / ACT_ENC_BATCH; part++) spend_encode_thread(&H->c, p, part, cpts.data(), items.data());
-    for (size_t p = 0; p < n; p++) spend_head_thread(&H->c, p, pf.data(), items.data(), cn.data(), kp.data(), flags.data());
     for (size_t p = 0; p < n; p++)
         for (int c = 0; c < ACT_SPEND_CHUNKS; c++) spend_chunk_thread(&H->c, p, c, items.data(), cvs.data());
     for (size_t p = 0; p < n; p++) spend_finish_thread(&H->c, p, pf.data(), cvs.data(), flags.data(), status);
