@@ -2,6 +2,9 @@ set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 make -C oracle -s > /dev/null 2>&1
-timeout 900 python tools/variant_bench.py 65536 base h2 base h2 > gpurun_out/variants17.txt 2>&1
-cat gpurun_out/variants17.txt | cut -c1-400
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+for v in b128 b32 b64 b128 b32; do
+  timeout 600 python tools/bench_variant.py $v --n-spend 524288 --n-issue 131072 --no-cpu-baseline --mixed-frac 0 --steps 3 --warmup 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v', round(d['value']), round(d['e2e']['value']), d['roofline']['kernel_ms']['spend_range'])"
+done > gpurun_out/variants18.txt 2>&1
+cat gpurun_out/variants18.txt
