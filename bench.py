@@ -36,10 +36,10 @@ UNIT = "proofs/s"
 # Algorithmic work per unit in 32x32+64->64 limb multiply-accumulates (field multiply M = 72, square S = 44), counted for
 # the algorithm this engine implements (DESIGN.md section 4 has the breakdown; SURVEY.md 8d estimated 4.8e7 / 7.0e5 for
 # a wNAF formulation -- the implemented shared-chain / wide-window / batched-encode algorithm needs less):
-#   range kernel per com_j: 1506 S + 2615 M = 2.545e5  -> x128 = 3.26e7 per proof
-#   encode 7.1e5, head 8.0e5 (A1 as a two-term sum, A-bar never formed), sign 3.9e5 (A and Y_A share a doubling chain) per proof
-LIMB_MACS_PER_SPEND_RANGE = 3.26e7
-LIMB_MACS_PER_SPEND = 3.26e7 + 7.1e5 + 8.0e5 + 3.9e5
+#   range kernel per com_j: 1506 S + 2583 M = 2.522e5  -> x128 = 3.23e7 per proof (T skipped on the last addition of a window)
+#   encode 7.1e5, head 8.2e5 (A1 as a two-term sum, A-bar never formed; the h2 terms of j = 0), sign 3.9e5 (A and Y_A share a doubling chain) per proof
+LIMB_MACS_PER_SPEND_RANGE = 3.23e7
+LIMB_MACS_PER_SPEND = 3.23e7 + 7.1e5 + 8.2e5 + 3.9e5
 LIMB_MACS_PER_ISSUE = 6.0e5
 # IMAD.WIDE.U32 issues at 32 lanes per clock per SM on sm_100 (ncu: 2 fma-heavy pipe cycles per warp instruction at
 # 0.5 instructions/clock/SMSP; profiles/r01d_*.txt) -> integer-multiply roofline = SMs x 32 x SM clock
@@ -351,7 +351,7 @@ def main():
                        "pipe rate from ncu (sm__pipe_fmaheavy_cycles_active: 2 cycles per IMAD.WIDE warp instruction); there is no integer entry in MEASURED_PEAKS.json",
         "peak_microbench": peak_microbench / 1e12,
         "peak_microbench_note": "act_measure_int_mul_peak: live IMAD.WIDE chain loop (includes ptxas register-pair moves on the same pipe, so it is a lower bound)",
-        "work_per_unit": f"{LIMB_MACS_PER_SPEND_RANGE:.3g} limb-MACs per proof in this kernel = 128 x (1506 S x 44 + 2615 M x 72), the implemented algorithm (DESIGN.md 4)",
+        "work_per_unit": f"{LIMB_MACS_PER_SPEND_RANGE:.3g} limb-MACs per proof in this kernel = 128 x (1506 S x 44 + 2583 M x 72), the implemented algorithm (DESIGN.md 4)",
         "timing": "separate pass, one stream, slices of 16384 proofs, CUDA events around every launch",
         "kernel_share_of_step": rng_ms / total_kernel_ms if total_kernel_ms else None,
         "kernel_ms": {k: round(v[0], 3) for k, v in ktimes.items() if v[1]},
