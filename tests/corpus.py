@@ -158,6 +158,66 @@ def mutate_proofs(ctx, base, seed=b"mut-pf"):
     return proofs.reshape(-1), rnd.reshape(-1), expect, labels
 
 
+def edge_issue_inputs(base):
+    """Valid requests with extreme credit amounts and degenerate signer randomness (src/tests.rs:642-689 large amounts,
+    :876-914 zero credit, :825-848 e = 0): c in {0, 1, 2^128 - 1, l - 1, l (non-canonical zero)}; rnd all-zero (e = alpha = 0:
+    Y_A and Y_G are the identity), all-ones, and e = 0 with a random alpha.  Returns (req, cs, rnd)."""
+    req = base["req"].reshape(-1, 128).copy(); cs = base["cs"].reshape(-1, 32).copy(); rnd = base["rnd"].reshape(-1, 128).copy()
+    n = len(req)
+    cvals = [0, 1, (1 << 128) - 1, ELL - 1, ELL]
+    for i in range(n):
+        cs[i] = np.frombuffer(cvals[i % len(cvals)].to_bytes(32, "little"), np.uint8)
+        m = (i // len(cvals)) % 4
+        if m == 1: rnd[i] = 0
+        elif m == 2: rnd[i] = 255
+        elif m == 3: rnd[i, :64] = 0
+    return req.reshape(-1), cs.reshape(-1), rnd.reshape(-1)
+
+
+def mutate_proofs_head(ctx, base):
+    """A second adversarial spend corpus aimed at the equations the engine computes differently from the reference
+    (src/lib.rs:791-799, 806-809, 825-829): A1 without A-bar, the h2 terms of C'_00 / C'_01 added by the head stage, A2, C.
+    Every class must fail the transcript comparison (status 7) unless noted; 255 = defer to the oracle.
+    Returns (proofs, rnd, expected_status, labels)."""
+    proofs = base["proofs"].reshape(-1, PROOF_BYTES).copy(); rnd = base["rnd"].reshape(-1, 128).copy()
+    n = len(proofs)
+    expect = np.zeros(n, np.uint8); labels = ["valid"] * n
+    rs = np.random.RandomState(23)
+    names = {133: "e_bar", 134: "r2_bar", 135: "r3_bar", 136: "c_bar", 137: "r_bar", 138: "w00", 139: "w01", 524: "k_bar", 525: "s_bar"}
+    idxs = sorted(names)
+    for i in range(n):
+        pf = proofs[i]
+        kind = i % 8
+        if kind == 0:      # valid proof signed with degenerate randomness: e = alpha = 0, all-ones, or e = 0 only
+            m = (i // 8) % 4
+            if m == 1: rnd[i] = 0
+            elif m == 2: rnd[i] = 255
+            elif m == 3: rnd[i, :64] = 0
+            labels[i] = "valid, rnd mode %d" % m
+        if kind == 1:      # one of the response scalars of the sigma protocol += 1
+            idx = idxs[(i // 8) % len(idxs)]
+            _set(pf, idx, sc_bytes(sc_int(_get(pf, idx)) + 1)); expect[i] = 7; labels[i] = names[idx] + "+1"
+        elif kind == 2:    # B_bar = identity: a VALID encoding (only A' is checked for identity, :787) -> transcript mismatch
+            _set(pf, 3, bytes(32)); expect[i] = 7; labels[i] = "B identity"
+        elif kind == 3:    # w00 / w01 = 0 or l-1: the h2 term of j = 0 vanishes or flips
+            idx = 138 + (i // 8) % 2
+            _set(pf, idx, sc_bytes(0 if (i // 16) % 2 else ELL - 1)); expect[i] = 7; labels[i] = names[idx] + " extreme"
+        elif kind == 4:    # A' and B_bar swapped (both valid points)
+            a, b = _get(pf, 2), _get(pf, 3); _set(pf, 2, b); _set(pf, 3, a); expect[i] = 7; labels[i] = "A'/B swapped"
+        elif kind == 5:    # non-canonical encodings of exactly the scalars the head stage combines with x: accepted, same outputs
+            for idx in (132, 133, 134, 138, 139):
+                v = sc_int(_get(pf, idx)) + ELL
+                if v < 2**256:
+                    _set(pf, idx, v.to_bytes(32, "little"))
+            labels[i] = "non-canonical head scalars"
+        elif kind == 6:    # com[0] replaced by com[1] (the only commitment with h2 terms loses its own base)
+            _set(pf, 4, _get(pf, 5)); expect[i] = 255; labels[i] = "com0 := com1"
+        elif kind == 7:    # gamma0[0] / z[0][b] changed: the j = 0 pair that the head stage completes
+            idx = (140, 268, 269)[(i // 8) % 3]
+            _set(pf, idx, sc_bytes(sc_int(_get(pf, idx)) + 1 + rs.randint(0, 1 << 20))); expect[i] = 7; labels[i] = "j=0 scalar"
+    return proofs.reshape(-1), rnd.reshape(-1), expect, labels
+
+
 def overspend_proofs(ctx, n, seed=b"overspend"):
     """prove_spend run with s > c (src/tests.rs:366-374,1540-1547) -> InvalidClientSpendProof."""
     rs = np.random.RandomState(5)

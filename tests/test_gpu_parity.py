@@ -77,6 +77,32 @@ def test_spend_refund_valid_and_mutated(engine, octx, base):
     assert 0 in st2.tolist() and 4 in st2.tolist()
 
 
+def test_head_stage_corpus(engine, octx):
+    """Mutations aimed at the equations the engine computes differently from the reference (A1 without A-bar, the h2 terms of
+    C'_00 / C'_01 added by the head kernel, A2, C): statuses, refunds and nullifiers equal the oracle's bit for bit."""
+    base = corpus.gen_valid(octx, 48, seed=b"gpu-head", threads=8)
+    proofs, rnd, expect, labels = corpus.mutate_proofs_head(octx, base)
+    ref, nul, st = engine.batch_verify_spend_and_refund(proofs, rnd)
+    o_ref, o_nul, o_st, _ = octx.batch_refund(proofs, rnd, threads=8)
+    assert st.tolist() == o_st.tolist()
+    assert (ref == o_ref).all() and (nul == o_nul).all()
+    for i, e in enumerate(expect):
+        if e != 255:
+            assert st[i] == e, (i, labels[i], st[i])
+    assert set(st.tolist()) == {0, 7}
+
+
+def test_issue_edge_credits_and_degenerate_randomness(engine, octx):
+    """c in {0, 1, 2^128-1, l-1, l}; signer randomness all-zero (e = alpha = 0: identity Y_A, Y_G), all-ones, e = 0."""
+    base = corpus.gen_valid(octx, 40, seed=b"gpu-edge", threads=8)
+    req, cs, rnd = corpus.edge_issue_inputs(base)
+    resp, st = engine.batch_issue(req, cs, rnd)
+    o_resp, o_st, _ = octx.batch_issue(req, cs, rnd, threads=8)
+    assert st.tolist() == o_st.tolist() == [0] * 40 and (resp == o_resp).all()
+    K = base["req"].reshape(-1, 128)[:, :32].copy().reshape(-1)
+    assert engine.batch_issuance_check(K, resp).tolist() == octx.batch_issuance_check(K, resp, threads=8)[0].tolist()
+
+
 def test_overspend_rejected(engine, octx):
     bad = corpus.overspend_proofs(octx, 8)
     ref, nul, st = engine.batch_verify_spend_and_refund(bad["proofs"], bad["rnd"])

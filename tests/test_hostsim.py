@@ -118,6 +118,33 @@ def test_issue_refund_parity_with_mutations(octx):
     assert st2.tolist() == o_st2.tolist() and st2[0] == 4
 
 
+def test_head_stage_corpus(octx):
+    """Mutations aimed at the equations the engine reformulates (A1 without A-bar, h2 terms in the head stage, A2, C):
+    host build of the device code == oracle, and every class carries the reference's error."""
+    base = corpus.gen_valid(octx, 24, seed=b"hostsim-head", threads=8)
+    hs = HS.Ctx(octx.h, octx.x, octx.w)
+    proofs, rnd, expect, labels = corpus.mutate_proofs_head(octx, base)
+    ref, nul, st = hs.refund(proofs, rnd)
+    o_ref, o_nul, o_st, _ = octx.batch_refund(proofs, rnd, threads=8)
+    assert st.tolist() == o_st.tolist()
+    assert (ref == o_ref).all() and (nul == o_nul).all()
+    for i, e in enumerate(expect):
+        if e != 255:
+            assert st[i] == e, (i, labels[i], st[i])
+    assert set(st.tolist()) == {0, 7}
+
+
+def test_issue_edge_credits_and_degenerate_randomness(octx):
+    base = corpus.gen_valid(octx, 20, seed=b"hostsim-edge", threads=8)
+    hs = HS.Ctx(octx.h, octx.x, octx.w)
+    req, cs, rnd = corpus.edge_issue_inputs(base)
+    resp, st = hs.issue(req, cs, rnd)
+    o_resp, o_st, _ = octx.batch_issue(req, cs, rnd, threads=8)
+    assert st.tolist() == o_st.tolist() == [0] * 20 and (resp == o_resp).all()
+    K = base["req"].reshape(-1, 128)[:, :32].copy().reshape(-1)
+    assert hs.issuance_check(K, resp).tolist() == octx.batch_issuance_check(K, resp, threads=8)[0].tolist()
+
+
 def test_golden_corpus_small():
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corpus_small.npz"))
     hs = HS.Ctx(g["h"].tobytes(), g["x"].tobytes(), g["w"].tobytes())
