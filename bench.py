@@ -353,6 +353,9 @@ def main():
         "peak_microbench_note": "act_measure_int_mul_peak: live IMAD.WIDE chain loop (includes ptxas register-pair moves on the same pipe, so it is a lower bound)",
         "work_per_unit": f"{LIMB_MACS_PER_SPEND_RANGE:.3g} limb-MACs per proof in this kernel = 128 x (1506 S x 44 + 2583 M x 72), the implemented algorithm (DESIGN.md 4)",
         "timing": "separate pass, one stream, slices of 16384 proofs, CUDA events around every launch",
+        "second_bound": "instruction issue: the IADD3 + IMAD.WIDE mix of a field multiplication tops out at 0.52-0.54 warp instructions per clock "
+                        "per SM sub-partition on B200 (tools/issue_bench.cu, profiles/r01j_micro_issue_rate.txt); the kernel runs at 0.45-0.47 "
+                        "(ncu, profiles/r01j_spend_range.txt) with the fma-heavy pipe 88-90 % busy",
         "kernel_share_of_step": rng_ms / total_kernel_ms if total_kernel_ms else None,
         "kernel_ms": {k: round(v[0], 3) for k, v in ktimes.items() if v[1]},
         "whole_step": {"achieved": LIMB_MACS_PER_SPEND * n * K / (ms * 1e-3) / 1e12, "frac": LIMB_MACS_PER_SPEND * n * K / (ms * 1e-3) / peak},
