@@ -273,6 +273,16 @@ __global__ void selftest_kernel(u32* fail) {
         // a * a^-1 == 1 (skip zero)
         if (!fe_is_zero(a)) { if (!fe_eq(fe_mul(a, fe_invert(a)), fe_one())) bad |= 8; }
         if (!fe_eq(fe_sq(a), fe_mul(a, a))) bad |= 16;
+        // products are tight, and the one-pass sum / double of two products agree with the general add
+        fe sq = fe_sq(a);
+        if (!fe_is_tight_(got) || !fe_is_tight_(sq)) bad |= 256;
+        if (!fe_eq(fe_add_tt(got, sq), fe_add(got, sq)) || !fe_eq(fe_dbl_tt(got), fe_add(got, got))) bad |= 512;
+        // the wrap-around branch of the tight operations: operands at the top of the tight range
+        fe hi1 = fe_zero(), hi2 = fe_zero();
+        hi1.v[7] = 0x80000000u; hi1.v[0] = 2047u - (u32)(it & 31);            // 2^255 + (2047 - k)
+        hi2.v[7] = 0x7fffffffu; for (int i = 0; i < 7; i++) hi2.v[i] = 0xffffffffu - (u32)(it * i);   // just below 2^255
+        if (!fe_eq(fe_add_tt(hi1, hi2), fe_add(hi1, hi2)) || !fe_eq(fe_add_tt(hi1, hi1), fe_add(hi1, hi1))) bad |= 1024;
+        if (!fe_eq(fe_dbl_tt(hi1), fe_add(hi1, hi1)) || !fe_eq(fe_dbl_tt(hi2), fe_add(hi2, hi2))) bad |= 2048;
     }
     // basepoint encodes to the RFC 9496 generator
     {

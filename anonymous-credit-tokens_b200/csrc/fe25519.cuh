@@ -37,6 +37,18 @@
 #ifndef ACT_REDUCE_ALT
 #define ACT_REDUCE_ALT 1
 #endif
+// ACT_TIGHT: products leave fe_fold9 "tight" (< 2^255 + 2^11: bit 255 is folded too, at no extra instruction), which lets
+// the sum or the double of two PRODUCTS skip the second carry pass (fe_add_tt / fe_dbl_tt below).
+#ifndef ACT_TIGHT
+#define ACT_TIGHT 1
+#endif
+// the host build (tests/hostsim) checks the precondition of the tight operations on every call
+#if !defined(__CUDA_ARCH__) && defined(ACT_HOSTSIM_CHECKS)
+#include <assert.h>
+#define ACT_ASSERT_TIGHT(x) assert(fe_is_tight_(x))
+#else
+#define ACT_ASSERT_TIGHT(x) ((void)0)
+#endif
 
 typedef uint32_t u32;
 typedef uint64_t u64;
@@ -159,6 +171,56 @@ ACT_FN fe fe_sub(const fe& a, const fe& b) {
 }
 ACT_FN fe fe_neg(const fe& a) { return fe_sub(fe_zero(), a); }
 
+// ---- sums of PRODUCTS -----------------------------------------------------------------------------
+// "tight" = below 2^255 + 2^11, which is what fe_mul / fe_sq return under ACT_TIGHT (fe_fold9).  The sum of two tight values
+// is below 2^256 + 2^12: if it wraps, what is left is below 2^12, so the 38 that the lost 2^256 is worth goes onto the low word
+// without a second carry pass.  The results are ordinary loose values (< 2^256).  Only for operands that ARE products; the
+// host build asserts it on every call (tests/hostsim, -DACT_HOSTSIM_CHECKS).
+ACT_FN bool fe_is_tight_(const fe& a) { return a.v[7] < 0x80000000u || (a.v[7] == 0x80000000u && !(a.v[6] | a.v[5] | a.v[4] | a.v[3] | a.v[2] | a.v[1]) && a.v[0] < 2048u); }
+#if ACT_TIGHT
+ACT_FN fe fe_add_tt(const fe& a, const fe& b) {
+    ACT_ASSERT_TIGHT(a); ACT_ASSERT_TIGHT(b);
+    fe r;
+#if ACT_PTX
+    u32 c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    r.v[0] += (0u - c) & 38u;
+#else
+    u64 c = 0;
+    for (int i = 0; i < 8; i++) { c += (u64)a.v[i] + b.v[i]; r.v[i] = (u32)c; c >>= 32; }
+    r.v[0] += (u32)c * 38u;
+#endif
+    return r;
+}
+// 2a for a tight a: a one-bit shift; the bit that leaves at the top is worth 38, and then what stays is below 2^12
+ACT_FN fe fe_dbl_tt(const fe& a) {
+    ACT_ASSERT_TIGHT(a);
+    fe r;
+#if ACT_PTX
+    ACT_UNROLL for (int i = 7; i >= 1; i--) r.v[i] = __funnelshift_l(a.v[i - 1], a.v[i], 1);
+    r.v[0] = (a.v[0] << 1) + ((0u - (a.v[7] >> 31)) & 38u);
+#else
+    for (int i = 7; i >= 1; i--) r.v[i] = (a.v[i] << 1) | (a.v[i - 1] >> 31);
+    r.v[0] = (a.v[0] << 1) + (a.v[7] >> 31) * 38u;
+#endif
+    return r;
+}
+#else
+ACT_FN fe fe_add_tt(const fe& a, const fe& b) { return fe_add(a, b); }
+ACT_FN fe fe_dbl_tt(const fe& a) { return fe_add(a, a); }
+#endif
+
 // ---- 8x8 -> 16 limb product ------------------------------------------------------------------
 #if ACT_PTX
 // acc[0..7] += {a0,a1,a2,a3} * bi placed in non-overlapping 64-bit slots, carry into acc[8]
@@ -191,9 +253,30 @@ ACT_FN void fe_row_chain_fresh(u32* acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 bi)
 }
 #endif
 
-// t[0..8] (value < 39 * 2^256) -> loosely reduced fe
+// t[0..8] (value < 39 * 2^256) -> fe.  ACT_TIGHT: everything from bit 255 up folds as 19 * (t >> 255): the result is
+// < 2^255 + 19 * 79 < 2^255 + 2^11 and the chain cannot carry out (word 7 is below 2^31 when the carry arrives); same
+// instruction count as folding at 2^256 (one shift + one mask replace the carry capture and its multiply).
 ACT_FN fe fe_fold9(u32* t) {
     fe r;
+#if ACT_TIGHT
+#if ACT_PTX
+    u32 f = __funnelshift_l(t[7], t[8], 1) * 19u, t7 = t[7] & 0x7fffffffu;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, 0;\n\t"
+        "addc.cc.u32 %2, %10, 0;\n\t"
+        "addc.cc.u32 %3, %11, 0;\n\t"
+        "addc.cc.u32 %4, %12, 0;\n\t"
+        "addc.cc.u32 %5, %13, 0;\n\t"
+        "addc.cc.u32 %6, %14, 0;\n\t"
+        "addc.u32 %7, %15, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t7), "r"(f));
+#else
+    u64 c = (u64)((t[8] << 1) | (t[7] >> 31)) * 19u;
+    t[7] &= 0x7fffffffu;
+    for (int i = 0; i < 8; i++) { c += t[i]; r.v[i] = (u32)c; c >>= 32; }
+#endif
+#else
 #if ACT_PTX
     u32 f = t[8] * 38u, c;
     asm("add.cc.u32 %0, %9, %17;\n\t"
@@ -212,6 +295,7 @@ ACT_FN fe fe_fold9(u32* t) {
     u64 c = (u64)t[8] * 38u;
     for (int i = 0; i < 8; i++) { c += t[i]; r.v[i] = (u32)c; c >>= 32; }
     r.v[0] += (u32)c * 38u;
+#endif
 #endif
     return r;
 }

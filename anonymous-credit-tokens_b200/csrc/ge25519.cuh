@@ -95,11 +95,11 @@ ACT_FN ge ge_add_cached_u(const ge& p, const ge_cached& q, u32 neg, bool want_t)
     // (statement and operand order chosen by the marshalling moves ptxas needs in the range kernel: 363 vs 381 instructions)
     fe TT = GE_MUL(p.T, q.T2d);
     fe ZZ = GE_MUL(p.Z, q.Z);
-    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe ZZ2 = fe_dbl_tt(ZZ);                              // ZZ, PP, MM are products: tight
     fe G0 = fe_add(ZZ2, TT), F0 = fe_sub(ZZ2, TT);
     fe PP = GE_MUL(fe_select(q.YpX, q.YmX, neg), fe_add(p.Y, p.X));
     fe MM = GE_MUL(fe_select(q.YmX, q.YpX, neg), fe_sub(p.Y, p.X));
-    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
+    fe E = fe_sub(PP, MM), H = fe_add_tt(PP, MM);
     fe G = fe_select(G0, F0, neg), F = fe_select(F0, G0, neg);
     ge r;
     r.X = GE_MUL(E, F); r.Z = GE_MUL(G, F); r.Y = GE_MUL(H, G);     // order chosen by the moves ptxas needs (369 vs 381 instructions)
@@ -112,7 +112,7 @@ ACT_GE_FN ge ge_add_niels(ge p, ge_niels q) {
     u32 zc_ = act_zero(); (void)zc_;
     fe PP = GE_MUL(fe_add(p.Y, p.X), q.ypx);
     fe MM = GE_MUL(fe_sub(p.Y, p.X), q.ymx);
-    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
+    fe E = fe_sub(PP, MM), H = fe_add_tt(PP, MM);
     fe TT = GE_MUL(p.T, q.xy2d);
     fe ZZ2 = fe_add(p.Z, p.Z);
     fe G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
@@ -125,7 +125,7 @@ ACT_FN ge ge_add_niels_n(const ge& p, const ge_niels& q, u32 neg) {
     u32 zc_ = act_zero(); (void)zc_;
     fe PP = GE_MUL(fe_add(p.Y, p.X), fe_select(q.ypx, q.ymx, neg));
     fe MM = GE_MUL(fe_sub(p.Y, p.X), fe_select(q.ymx, q.ypx, neg));
-    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
+    fe E = fe_sub(PP, MM), H = fe_add_tt(PP, MM);      // PP, MM are products: tight
     fe TT = GE_MUL(p.T, q.xy2d);
     fe ZZ2 = fe_add(p.Z, p.Z);
     fe G0 = fe_add(ZZ2, TT), F0 = fe_sub(ZZ2, TT);
@@ -170,9 +170,9 @@ ACT_FN ge ge_dbl(const ge& p, bool want_t) { return want_t ? ge_dbl_t(p) : ge_db
 ACT_FN ge ge_dbl_u(const ge& p, bool want_t) {
     u32 zc_ = act_zero(); (void)zc_;
     fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y);
-    fe Yc = fe_add(YY, XX), Zc = fe_sub(YY, XX);
+    fe Yc = fe_add_tt(YY, XX), Zc = fe_sub(YY, XX);     // XX, YY, ZZ are products: tight
     fe ZZ = GE_SQ(p.Z);
-    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe ZZ2 = fe_dbl_tt(ZZ);
     fe Tc = fe_sub(ZZ2, Zc);
     fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
     fe Xc = fe_sub(XpY2, Yc);

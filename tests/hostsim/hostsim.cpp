@@ -133,6 +133,15 @@ EXPORT void hs_fe_mul(const uint8_t a[32], const uint8_t b[32], uint8_t out[32])
     fe x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32);  // full 256-bit loose inputs allowed
     fe z = fe_mul(x, y); u32 w[8]; fe_to_words(w, z); memcpy(out, w, 32);
 }
+// raw words of a*b, a^2 (as the multiplication leaves them: must be "tight"), and of the tight sum / double of those two
+EXPORT int hs_fe_tight(const uint8_t a[32], const uint8_t b[32], uint8_t prod[32], uint8_t sq[32], uint8_t sum[32], uint8_t dbl[32]) {
+    fe x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32);
+    fe m = fe_mul(x, y), q = fe_sq(x);
+    int tight = fe_is_tight_(m) && fe_is_tight_(q);
+    fe sm = fe_add_tt(m, q), d = fe_dbl_tt(m);
+    memcpy(prod, m.v, 32); memcpy(sq, q.v, 32); memcpy(sum, sm.v, 32); memcpy(dbl, d.v, 32);
+    return tight;
+}
 EXPORT void hs_fe_addsub(const uint8_t a[32], const uint8_t b[32], uint8_t sum[32], uint8_t diff[32]) {
     fe x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32);
     u32 w[8]; fe_to_words(w, fe_add(x, y)); memcpy(sum, w, 32); fe_to_words(w, fe_sub(x, y)); memcpy(diff, w, 32);

@@ -31,6 +31,32 @@ def test_field_arithmetic_loose_inputs():
             assert int.from_bytes(HS.call1("hs_fe_invert", b32(a)), "little") == pow(a, -1, P)
 
 
+def test_products_are_tight_and_tight_sums_are_exact():
+    """fe_mul / fe_sq leave values below 2^255 + 2^11 whatever the (loose) inputs; the one-pass sum and double of two such
+    values (fe_add_tt, fe_dbl_tt) are below 2^256 and congruent to the true sum / double."""
+    import ctypes as C
+    rnd = random.Random(2)
+    edge = [0, 1, 19, P - 1, P, P + 1, 2 * P - 1, 2 * P, 2 * P + 37, 2**255 - 1, 2**255, 2**255 + 2047, 2**256 - 1, 2**256 - 38]
+    # inputs whose product is = -1, -2, ... (mod p) push the result to the top of the range: a * a^-1 * (p - k)
+    near = []
+    for k in (1, 2, 19, 20, 37, 38, 39):
+        a = rnd.getrandbits(255) % P or 3
+        near.append((a, pow(a, -1, P) * (P - k) % P))
+    pairs = [(a, b) for a in edge for b in edge] + near + [(rnd.getrandbits(256), rnd.getrandbits(256)) for _ in range(400)]
+    lib = HS.lib()
+    lib.hs_fe_tight.restype = C.c_int
+    lib.hs_fe_tight.argtypes = [C.c_void_p] * 6
+    for a, b in pairs:
+        ia, ib = HS._in(b32(a)), HS._in(b32(b))
+        outs = [HS._out(32) for _ in range(4)]
+        tight = lib.hs_fe_tight(ia[1], ib[1], *[o[1] for o in outs])
+        m, q, sm, d = [int.from_bytes(o[0].tobytes(), "little") for o in outs]
+        assert tight == 1 and m < 2**255 + 2**11 and q < 2**255 + 2**11
+        assert m % P == a * b % P and q % P == a * a % P
+        assert sm < 2**256 and sm % P == (m + q) % P
+        assert d < 2**256 and d % P == 2 * m % P
+
+
 def test_scalar_arithmetic():
     rnd = random.Random(2)
     for it in range(100):
