@@ -78,10 +78,10 @@ ACT_GE_FN ge ge_add_cached(ge p, ge_cached q) {
     u32 zc_ = act_zero(); (void)zc_;
     fe PP = GE_MUL(fe_add(p.Y, p.X), q.YpX);
     fe MM = GE_MUL(fe_sub(p.Y, p.X), q.YmX);
-    fe E = fe_sub(PP, MM), H = fe_add(PP, MM);
+    fe E = fe_sub(PP, MM), H = fe_add_tt(PP, MM);
     fe TT = GE_MUL(p.T, q.T2d);
     fe ZZ = GE_MUL(p.Z, q.Z);
-    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe ZZ2 = fe_dbl_tt(ZZ);
     fe G = fe_add(ZZ2, TT), F = fe_sub(ZZ2, TT);
     ge r;
     r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
@@ -142,9 +142,9 @@ ACT_FN ge ge_sub(const ge& p, const ge& q) { return ge_add_cached(p, ge_to_cache
 ACT_GE_FN ge ge_dbl_t(ge p) {
     u32 zc_ = act_zero(); (void)zc_;
     fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y), ZZ = GE_SQ(p.Z);
-    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe ZZ2 = fe_dbl_tt(ZZ);
     fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
-    fe Yc = fe_add(YY, XX), Zc = fe_sub(YY, XX);
+    fe Yc = fe_add_tt(YY, XX), Zc = fe_sub(YY, XX);
     fe Xc = fe_sub(XpY2, Yc), Tc = fe_sub(ZZ2, Zc);
     ge r;
     r.X = GE_MUL(Xc, Tc); r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Zc, Tc); r.T = GE_MUL(Xc, Yc);
@@ -154,9 +154,9 @@ ACT_GE_FN ge ge_dbl_t(ge p) {
 ACT_GE_FN ge ge_dbl_not(ge p) {
     u32 zc_ = act_zero(); (void)zc_;
     fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y), ZZ = GE_SQ(p.Z);
-    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe ZZ2 = fe_dbl_tt(ZZ);
     fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
-    fe Yc = fe_add(YY, XX), Zc = fe_sub(YY, XX);
+    fe Yc = fe_add_tt(YY, XX), Zc = fe_sub(YY, XX);
     fe Xc = fe_sub(XpY2, Yc), Tc = fe_sub(ZZ2, Zc);
     ge r;
     r.X = GE_MUL(Xc, Tc); r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Zc, Tc); r.T = p.T;
