@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(ACT_ISSUE_BLOCK, ACT_ISSUE_BPS) issuance_check
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) issuance_check_thread(C, i, K, resp, status);
 }
-// One block of 128 threads works on one proof at a time: thread j owns com_j and the pair C'_j0, C'_j1.  The grid is
-// sized to the machine (SMs x resident blocks) and strides over the chunk, so the per-thread window tables live in a
-// scratch buffer indexed by (block, thread) that stays small enough to sit in L2 whatever the batch size.
+// The range kernel: a thread owns one com_j and the pair C'_j0, C'_j1; a warp owns 32 consecutive j of one proof.  The grid
+// is persistent and sized to the machine (SMs x resident blocks), so the per-thread window tables live in a scratch buffer
+// indexed by (block, thread) whose size does not depend on the batch.
 #ifndef ACT_RANGE_BLOCKS_PER_SM
 #define ACT_RANGE_BLOCKS_PER_SM 4   // 128 registers per thread; measured 153k vs 146k proofs/s at 3
 #endif
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(ACT_ISSUE_BLOCK, ACT_ISSUE_BPS) issuance_check
 // assignment of whole proofs to blocks, the warps of one SM finish the SAME amount of work between 60 ms and 96 ms after
 // launch -- the warp scheduler is not fair between warps -- so on average only 79 % of the launched warps were resident;
 // drawing units on demand keeps 98 % resident (a favoured warp simply draws up to 3x the units of a starved one) and
-// also spreads the two extra fixed-base terms of lane j = 0.  ACT_RANGE_DYNAMIC=0 is the static form (block = 128 only).
+// evens out whatever else differs between warps.  ACT_RANGE_DYNAMIC=0 is the static form (block = 128 only).
 #ifndef ACT_RANGE_DYNAMIC
 #define ACT_RANGE_DYNAMIC 1
 #endif

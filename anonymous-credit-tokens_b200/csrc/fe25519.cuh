@@ -1,7 +1,7 @@
 // fe25519.cuh -- GF(2^255-19) on 8 saturated 32-bit limbs (radix 2^32) for sm_100a.
 //
 // Values are kept "loosely reduced": any representative in [0, 2^256).  2^256 = 38 (mod p), so a
-// 512-bit product folds as lo + 38*hi.  The 8x8 limb product runs on the integer multiply pipe as
+// 512-bit product folds as lo + 38*hi; its last fold starts at bit 255, so products are below 2^255 + 2^11.  The 8x8 limb product runs on the integer multiply pipe as
 // IMAD.WIDE.U32(.X) chains: mad.lo.cc/madc.hi.cc pairs of one (a_j, b_i) fuse into a single
 // 32x32+64 -> 64 multiply-add with carry-in/out predicates (checked with cuobjdump -sass), and the
 // even/odd column split keeps every chain free of overlapping 64-bit slots.
