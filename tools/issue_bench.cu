@@ -2,7 +2,8 @@
 // Independent accumulator streams (no dependency within 8 instructions), 16 warps per SM (4 per sub-partition) or 32,
 // operands varied so that nothing folds.  Modes: 0 IADD3 (3 register sources)  1 IADD (2 register sources)
 // 2 LOP3 (3 sources)  3 IMAD.WIDE.U32 with a 64-bit addend  4 alternating IADD3 / IMAD.WIDE (the mix of a field multiply)
-// 5 LOP3 with 2 register sources  6 IMAD (32-bit) with 3 register sources;  warpsN = N warps per sub-partition
+// 5 LOP3 with 2 register sources  6 IMAD (32-bit) with 3 register sources  7 IMAD.WIDE without addend  8-11 other mixes;
+// warpsN = N warps per sub-partition
 // Output: one JSON object; inst/clk/SMSP = instructions / (elapsed x SM clock x SMs x 4).
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -31,6 +32,15 @@ __global__ void __launch_bounds__(128) k(u32* out, u32 a0, u32 b0) {
                                  else asm volatile("{.reg .u32 t; add.u32 t, %1, %2; add.u32 %0, %0, t;}" : "+r"(r[i]) : "r"(x), "r"(y)); }
                 if (MODE == 5) asm volatile("xor.b32 %0, %1, %2;" : "=r"(r[i]) : "r"(x), "r"(r[(i + 3) & 7]));                      // LOP3, 2 sources
                 if (MODE == 6) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r[i]) : "r"(x), "r"(y));                            // IMAD, 3 sources
+                if (MODE == 7) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"((u32)w[(i + 1) & 7]), "r"((u32)(w[(i + 2) & 7] >> 32)));   // IMAD.WIDE, no addend
+                if (MODE == 8) { if ((i & 3) == 3) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((u32)w[(i + 4) & 7]), "r"(x));
+                                 else asm volatile("{.reg .u32 t; add.u32 t, %1, %2; add.u32 %0, %0, t;}" : "+r"(r[i]) : "r"(x), "r"(y)); }        // 3 IADD3 : 1 IMAD.WIDE
+                if (MODE == 9) { if ((i & 3) == 0) asm volatile("{.reg .u32 t; add.u32 t, %1, %2; add.u32 %0, %0, t;}" : "+r"(r[i]) : "r"(x), "r"(y));
+                                 else asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((u32)w[(i + 1) & 7]), "r"((u32)(w[(i + 2) & 7] >> 32))); } // 1 IADD3 : 3 IMAD.WIDE
+                if (MODE == 10) { if (i & 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((u32)w[(i + 2) & 7]), "r"((u32)(w[(i + 4) & 7] >> 32)));
+                                  else asm volatile("add.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(x)); }                                          // 1 two-source add : 1 IMAD.WIDE
+                if (MODE == 11) { if (i & 1) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"((u32)w[(i + 2) & 7]), "r"((u32)(w[(i + 4) & 7] >> 32)));
+                                  else asm volatile("{.reg .u32 t; add.u32 t, %1, %2; add.u32 %0, %0, t;}" : "+r"(r[i]) : "r"(x), "r"(y)); }      // 1 IADD3 : 1 IMAD.WIDE without addend
             }
         }
     }
@@ -49,12 +59,13 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     int clk_khz = 0; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
     u32* out; cudaMalloc(&out, 148 * 8 * 128 * 4 * 2);
-    const char* names[7] = {"iadd3_3reg", "iadd_2reg", "lop3_3reg", "imad_wide_64acc", "mix_iadd3_imadwide", "lop3_2reg", "imad_3reg"};
+    const char* names[12] = {"iadd3_3reg", "iadd_2reg", "lop3_3reg", "imad_wide_64acc", "mix_iadd3_imadwide", "lop3_2reg", "imad_3reg",
+                             "imad_wide_noacc", "mix_3iadd3_1wide", "mix_1iadd3_3wide", "mix_add2_wide", "mix_iadd3_wide_noacc"};
     printf("{\"sms\": %d, \"clock_khz\": %d", p.multiProcessorCount, clk_khz);
     for (int bps = 4; bps <= 8; bps *= 2) {
         int grid = p.multiProcessorCount * bps;
         double inst = (double)grid * 4 /*warps*/ * ITER * 32.0;   // warp instructions of the measured kind per launch
-        double ms[7];
+        double ms[12];
         ms[0] = time_ms([&] { k<0><<<grid, 128>>>(out, 3, 5); });
         ms[1] = time_ms([&] { k<1><<<grid, 128>>>(out, 3, 5); });
         ms[2] = time_ms([&] { k<2><<<grid, 128>>>(out, 3, 5); });
@@ -62,7 +73,12 @@ int main() {
         ms[4] = time_ms([&] { k<4><<<grid, 128>>>(out, 3, 5); });
         ms[5] = time_ms([&] { k<5><<<grid, 128>>>(out, 3, 5); });
         ms[6] = time_ms([&] { k<6><<<grid, 128>>>(out, 3, 5); });
-        for (int m = 0; m < 7; m++)
+        ms[7] = time_ms([&] { k<7><<<grid, 128>>>(out, 3, 5); });
+        ms[8] = time_ms([&] { k<8><<<grid, 128>>>(out, 3, 5); });
+        ms[9] = time_ms([&] { k<9><<<grid, 128>>>(out, 3, 5); });
+        ms[10] = time_ms([&] { k<10><<<grid, 128>>>(out, 3, 5); });
+        ms[11] = time_ms([&] { k<11><<<grid, 128>>>(out, 3, 5); });
+        for (int m = 0; m < 12; m++)
             printf(", \"%s_warps%d\": %.4f", names[m], bps, inst / (ms[m] * 1e-3) / ((double)clk_khz * 1e3) / (p.multiProcessorCount * 4.0));
     }
     printf("}\n");
