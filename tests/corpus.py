@@ -258,3 +258,130 @@ def prover_stream(seed32: bytes, index: int) -> bytes:
     """The derived RNG stream of act_batch_prove_spend: BLAKE3-XOF(seed || u64le(index)), 524 x 64 bytes."""
     import blake3
     return blake3.blake3(bytes(seed32) + int(index).to_bytes(8, "little")).digest(length=524 * 64)
+
+
+# ---- multi-generation token lifecycles (the scenario tests of src/tests.rs) ----
+# (label, credits at issuance, amounts spent one after the other).  A spend above the balance is produced by the prover
+# and rejected by the issuer (InvalidClientSpendProof); the client then keeps its old token.
+LIFECYCLES = [
+    ("sequential_spends", 100, [30, 20, 50, 1]),                                  # src/tests.rs:260-337 (+ one spend from the emptied token)
+    ("spend_exact_balance", 50, [50, 0]),                                         # :210-257
+    ("zero_spend_scenario", 100, [0, 100]),                                       # :378-426
+    ("token_with_zero_credit", 0, [7, 0, 0]),                                     # :876-914
+    ("exhaust_token_with_one_credit_spends", 5, [1, 1, 1, 1, 1, 1]),              # :917-1005
+    ("large_amount_issuance", 2**120 + 0x1234567890abcdef, [2**119 + 99, 2**119 - 5, 2**60]),   # :642-689
+    ("test_binary_decomposition_max_value", 2**128 - 1, [1, 2**128 - 2, 1]),      # :1008-1059
+    ("attempt_overspend", 10, [11, 2**127, 10]),                                  # :340-375, then the honest spend still works
+]
+
+
+class OracleImpl:
+    """The oracle behind the batch-shaped interface run_lifecycles() drives (also satisfied by hostsim_lib.Ctx and by
+    the GPU engine through EngineImpl)."""
+
+    def __init__(self, ctx):
+        self.c = ctx
+
+    def request(self, pre, rnd):
+        n = len(pre) // 64
+        return np.frombuffer(b"".join(self.c.request(pre[64 * i:64 * i + 64], rnd[128 * i:128 * i + 128]) for i in range(n)), np.uint8)
+
+    def issue(self, req, cs, rnd):
+        resp, st, _ = self.c.batch_issue(np.ascontiguousarray(req), np.ascontiguousarray(cs), np.ascontiguousarray(rnd))
+        return resp, st
+
+    def issuance_check(self, K, resp):
+        return self.c.batch_issuance_check(np.ascontiguousarray(K), np.ascontiguousarray(resp))[0]
+
+    def prove_spend(self, tokens, charges, rnd):
+        n = len(tokens) // 160
+        out = [self.c.prove_spend(tokens[160 * i:160 * i + 160], charges[32 * i:32 * i + 32], rnd[O.RND_PROVE * i:O.RND_PROVE * (i + 1)])
+               for i in range(n)]
+        f = lambda k: np.frombuffer(b"".join(o[k] for o in out), np.uint8)
+        return f(0), f(1), np.zeros(n, np.uint8)
+
+    def refund(self, proofs, rnd):
+        ref, nul, st, _ = self.c.batch_refund(np.ascontiguousarray(proofs), np.ascontiguousarray(rnd))
+        return ref, nul, st
+
+    def refund_check(self, com, refund):
+        return self.c.batch_refund_check(np.ascontiguousarray(com), np.ascontiguousarray(refund))[0]
+
+
+class EngineImpl:
+    """The GPU engine (host-buffer C ABI calls) behind the same interface."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def request(self, pre, rnd):
+        return self.e.batch_request(pre, rnd)
+
+    def issue(self, req, cs, rnd):
+        return self.e.batch_issue(req, cs, rnd)
+
+    def issuance_check(self, K, resp):
+        return self.e.batch_issuance_check(K, resp)
+
+    def prove_spend(self, tokens, charges, rnd):
+        return self.e.batch_prove_spend(tokens, charges, rnd=rnd)
+
+    def refund(self, proofs, rnd):
+        return self.e.batch_verify_spend_and_refund(proofs, rnd)
+
+    def refund_check(self, com, refund):
+        return self.e.batch_refund_check(com, refund)
+
+
+def run_lifecycles(impl, seed=b"lifecycle-0", scenarios=LIFECYCLES):
+    """Drives every scenario through request -> issue -> issuance_check and then, generation after generation,
+    prove_spend -> refund -> refund_check -> new token (A* | e* | k* | r* | m; PreRefund::to_credit_token,
+    src/lib.rs:1245-1252).  All scenarios advance together, one batch per generation.  Asserts the outcomes the reference's
+    tests assert (accept iff s <= balance, new balance = c - s, fresh nullifier every generation) and returns every byte the
+    issuer or the client produced, so that two implementations can be compared for equality."""
+    u8 = lambda b: np.frombuffer(bytes(b), np.uint8).copy()
+    n = len(scenarios)
+    le32 = lambda vals: u8(b"".join(int(v).to_bytes(32, "little") for v in vals))
+    pre = u8(b"".join(O.sc_reduce64(xof(seed + b"/r/%d" % i, 64)) + O.sc_reduce64(xof(seed + b"/k/%d" % i, 64)) for i in range(n)))
+    req = np.asarray(impl.request(pre, u8(xof(seed + b"/req", 128 * n))))
+    cs = le32([c for _, c, _ in scenarios])
+    resp, st = impl.issue(req, cs, u8(xof(seed + b"/issue", 128 * n)))
+    resp = np.asarray(resp)
+    assert (np.asarray(st) == 0).all(), st
+    assert (np.asarray(impl.issuance_check(req.reshape(n, 128)[:, :32].reshape(-1).copy(), resp)) == 0).all()
+    r2 = resp.reshape(n, 160); p2 = pre.reshape(n, 64)
+    tokens = [bytes(r2[i, :64]) + bytes(p2[i, 32:64]) + bytes(p2[i, :32]) + bytes(cs[32 * i:32 * i + 32]) for i in range(n)]
+    balance = [c for _, c, _ in scenarios]
+    seen = set()
+    log = dict(req=req.tobytes(), resp=resp.tobytes(), generations=[])
+    for g in range(max(len(s) for _, _, s in scenarios)):
+        live = [i for i in range(n) if g < len(scenarios[i][2])]
+        amounts = [scenarios[i][2][g] for i in live]
+        m = len(live)
+        proofs, prer, pst = impl.prove_spend(u8(b"".join(tokens[i] for i in live)), le32(amounts),
+                                             u8(xof(seed + b"/prove/%d" % g, O.RND_PROVE * m)))
+        proofs, prer = np.asarray(proofs), np.asarray(prer)
+        assert (np.asarray(pst) == 0).all()
+        ref, nul, vst = impl.refund(proofs, u8(xof(seed + b"/refund/%d" % g, 128 * m)))
+        ref, nul, vst = np.asarray(ref), np.asarray(nul), np.asarray(vst)
+        com = proofs.reshape(m, PROOF_BYTES)[:, 128:128 + 4096].reshape(-1).copy()
+        cst = np.asarray(impl.refund_check(com, ref))
+        for j, i in enumerate(live):
+            label, s = scenarios[i][0], amounts[j]
+            if s <= balance[i]:
+                assert vst[j] == 0 and cst[j] == 0, (label, g, int(vst[j]), int(cst[j]))
+                k = bytes(nul[32 * j:32 * j + 32])
+                assert k == tokens[i][64:96] and k not in seen, (label, g)       # nullifier() = the spent token's k, never seen before
+                seen.add(k)
+                q = bytes(prer[96 * j:96 * j + 96])
+                balance[i] -= s
+                assert int.from_bytes(q[64:96], "little") == balance[i], (label, g)
+                tokens[i] = bytes(ref[128 * j:128 * j + 64]) + q
+            else:
+                assert vst[j] == 7, (label, g, int(vst[j]))                       # InvalidClientSpendProof
+                assert not ref[128 * j:128 * j + 128].any() and not nul[32 * j:32 * j + 32].any()
+                assert cst[j] != 0                                                 # an all-zero refund never verifies
+        log["generations"].append(dict(proofs=proofs.tobytes(), prerefunds=prer.tobytes(), refunds=ref.tobytes(),
+                                       nullifiers=nul.tobytes(), status=vst.tobytes(), check=cst.tobytes()))
+    log["final_balances"] = balance
+    return log

@@ -374,6 +374,13 @@ def test_client_generators_on_gpu(act, engine, octx):
     assert (vst[:64] == 7).all()
 
 
+def test_token_lifecycles_match_the_oracle(engine, octx):
+    """Multi-generation token chains (corpus.LIFECYCLES: the reference's scenario tests, src/tests.rs:210-426,642-689,
+    876-1059) through the C ABI: request, issue, issuance_check, prove_spend, verify+refund, refund_check generation
+    after generation; every byte equals the oracle's."""
+    assert corpus.run_lifecycles(corpus.EngineImpl(engine)) == corpus.run_lifecycles(corpus.OracleImpl(octx))
+
+
 def test_sequential_rng_contract(engine, octx, base):
     """act_batch_*_seq == a loop of reference calls over ONE shared RNG: randomness is consumed only by accepted
     requests, in slice order (src/lib.rs:638-643, 842-846)."""

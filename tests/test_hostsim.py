@@ -244,3 +244,16 @@ def test_client_generators_match_the_oracle_prover(octx):
     bad = tokens.copy(); bad[:32] = np.frombuffer(corpus.bad_point_encodings()[0], np.uint8)
     p3, r3, s3 = hs.prove_spend(bad, charges, seed=seed)
     assert s3.tolist() == [0x81, 0, 0] and not p3[:corpus.PROOF_BYTES].any() and (p3[corpus.PROOF_BYTES:] != 0).any()
+
+
+def test_token_lifecycles_match_the_oracle(octx):
+    """Multi-generation token chains (corpus.LIFECYCLES, the reference's scenario tests) on the host build of the device
+    code: every proof, refund, nullifier and status equals the oracle's."""
+    hs = HS.Ctx(octx.h, octx.x, octx.w)
+
+    class Impl:
+        request = staticmethod(hs.request); issue = staticmethod(hs.issue); issuance_check = staticmethod(hs.issuance_check)
+        refund = staticmethod(hs.refund); refund_check = staticmethod(hs.refund_check)
+        prove_spend = staticmethod(lambda tokens, charges, rnd: hs.prove_spend(tokens, charges, rnd=rnd))
+
+    assert corpus.run_lifecycles(Impl) == corpus.run_lifecycles(corpus.OracleImpl(octx))

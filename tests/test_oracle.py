@@ -209,3 +209,14 @@ def test_oracle_vs_independent_stack_on_corpus(octx):
         rf = R.refund(H, x, octx.w, d, R.Rng(rnd))
         st, ref, nul = octx.refund(pf, rnd)
         assert st == 0 and isinstance(rf, dict) and R.pack_refund(rf) == ref
+
+
+def test_token_lifecycles(octx):
+    """The reference's scenario tests (sequential spends, exact balance, zero spend, zero-credit token, one-credit
+    exhaustion, 2^120 and 2^128-1 credit tokens, overspend; src/tests.rs:210-426,642-689,876-1059) as multi-generation
+    chains on the oracle: every generation's refund becomes the next token."""
+    log = corpus.run_lifecycles(corpus.OracleImpl(octx))
+    assert log["final_balances"] == [0, 0, 0, 0, 0, 0x1234567890abcdef - 94 - 2**60, 0, 0]
+    # determinism: same seeds, same bytes
+    again = corpus.run_lifecycles(corpus.OracleImpl(octx), scenarios=corpus.LIFECYCLES[:2])
+    assert again["generations"][0]["refunds"][:128] == log["generations"][0]["refunds"][:128]
