@@ -253,6 +253,7 @@ def main():
     torch.cuda.synchronize()
     assert bool((d_pst == 0).all())
     d_rnd = rbytes(n * 128)
+    d_tokens = tokens          # kept for the mixed batch (a second, different proof from an already spent token)
     del d_resp_s, d_ist_s, d_prer, d_pst, tokens, pre, d_req_s, d_cs_s
     log(f"[bench] rank {rank}: {n} unique tokens issued and spent on the device in {time.time() - t_gen:.1f}s")
     d_ref = torch.zeros(n * 128, dtype=torch.uint8, device=dev)
@@ -403,7 +404,7 @@ def main():
         sel = torch.rand(n, device=dev, generator=gen) < args.mixed_frac
         sel[0] = False
         tidx = torch.nonzero(sel).view(-1)
-        cls = torch.randint(0, 5, (tidx.numel(),), device=dev, generator=gen)
+        cls = torch.randint(0, 7, (tidx.numel(),), device=dev, generator=gen)
         saved = pv[tidx].clone()
         expect = torch.zeros(n, dtype=torch.uint8, device=dev)
         i0 = tidx[cls == 0]; pv[i0, 32] ^= 1; expect[i0] = 7                      # s changed            -> InvalidClientSpendProof
@@ -411,23 +412,65 @@ def main():
         bad = torch.tensor(list(((1 << 255) - 19).to_bytes(32, "little")), dtype=torch.uint8, device=dev)
         i2 = tidx[cls == 2]; pv[i2, 128 + 32 * 77:128 + 32 * 78] = bad; expect[i2] = 0x81   # com[77] = non-canonical p -> decode error
         i3 = tidx[cls == 3]; pv[i3, 32 * 132 + 3] ^= 0x40; expect[i3] = 7          # gamma bit flip       -> InvalidClientSpendProof
-        i4 = tidx[cls == 4]; pv[i4] = pv[i4 - 1]                                   # replay of the neighbour (still Ok for refund())
-        expect[i4] = expect[i4 - 1]
+        # same token spent twice with DIFFERENT proofs (same k, other charge and randomness): refund() says Ok, the screen must flag it
+        i5 = tidx[cls == 5]
+        m5 = int(i5.numel())
+        if m5:
+            tok5 = d_tokens[i5 - 1].contiguous()
+            ch5 = le32(torch.ones(m5, dtype=torch.int64, device=dev), m5)
+            pf5 = torch.empty(m5 * PROOF_BYTES, dtype=torch.uint8, device=dev)
+            pr5 = torch.empty(m5 * 96, dtype=torch.uint8, device=dev); ps5 = torch.empty(m5, dtype=torch.uint8, device=dev)
+            eng.batch_prove_spend_dev(m5, tok5.data_ptr(), ch5.data_ptr(), None, bytes(range(100, 132)), (world + rank) * n, pf5.data_ptr(), pr5.data_ptr(), ps5.data_ptr(), stream)
+            torch.cuda.synchronize()
+            assert bool((ps5 == 0).all())
+            pv[i5] = pf5.view(m5, PROOF_BYTES)
+            del tok5, ch5, pf5, pr5, ps5
+        # non-canonical scalar encodings (k + l, r_bar + l, gamma0[5] + l): accepted after reduction, nullifier = the reduced k (src/cbor.rs:80-91)
+        i6 = tidx[cls == 6]
+        ell = torch.tensor(list(corpus.ELL.to_bytes(32, "little")), dtype=torch.int64, device=dev)
+        for item in (0, 137, 145):
+            v = pv[i6, 32 * item:32 * item + 32].to(torch.int64) + ell
+            for b in range(31):
+                v[:, b + 1] += v[:, b] >> 8
+                v[:, b] &= 0xff
+            assert bool((v[:, 31] < 256).all())
+            pv[i6, 32 * item:32 * item + 32] = v.to(torch.uint8)
+        k6 = saved[cls == 6][:, :32].clone()
+        i4 = tidx[cls == 4]; src4 = pv[i4 - 1].clone(); exp4 = expect[i4 - 1].clone()  # exact replay of the neighbour (still Ok for refund())
+        pv[i4] = src4; expect[i4] = exp4
+        del src4
         mms = timed(spend_step, 1, K)
         st_m = d_st.clone()
         ok_status = bool((st_m == expect).all())
+        ok_nul6 = bool((d_nul.view(n, 32)[i6] == k6).all())
+        ok_nul5 = bool((d_nul.view(n, 32)[i5] == d_tokens[i5 - 1][:, 64:96]).all())
         d_flag = torch.empty_like(d_st)
         eng.flag_replays_dev(n, d_st.data_ptr(), d_nul.data_ptr(), 0, None, d_flag.data_ptr(), stream)
         torch.cuda.synchronize()
+        sharding = importlib.import_module("anonymous-credit-tokens_b200.sharding")
+        flag_ref = sharding.flag_replays(d_st, d_nul)          # sort-based torch formulation: the semantic reference of the screen
+        ok_flags = bool((d_flag == flag_ref).all())
         replays = int((d_flag == 3).sum().item())
+        # the oracle re-checks a sample of each class that must ACCEPT although it was touched (classes 5, 6)
+        samp = torch.cat([i5[:2], i6[:2]]).cpu().numpy()
+        if len(samp):
+            sp_ = pv[torch.as_tensor(samp, device=dev)].reshape(-1).cpu().numpy(); sr_ = d_rnd.view(n, 128)[torch.as_tensor(samp, device=dev)].reshape(-1).cpu().numpy()
+            o_ref5, o_nul5, o_st5, _ = ctx.batch_refund(sp_, sr_, threads=len(samp))
+            assert (o_st5 == 0).all() and (o_ref5.reshape(-1, 128) == d_ref.view(n, 128)[torch.as_tensor(samp, device=dev)].cpu().numpy()).all() \
+                and (o_nul5.reshape(-1, 32) == d_nul.view(n, 32)[torch.as_tensor(samp, device=dev)].cpu().numpy()).all(), "mixed batch: accepted-class output differs from oracle"
         mixed = {"value": world * n * K / (mms * 1e-3), "unit": UNIT, "tampered_fraction": float(sel.float().mean().item()),
-                 "classes": "s changed, A' identity, malformed com point, gamma bit flip, replayed proof (uniform)",
-                 "status_matches_expectation": ok_status, "accepted": int((st_m == 0).sum().item()),
+                 "classes": "s changed, A' identity, malformed com point, gamma bit flip, exact replay of the neighbour, same token spent again with a different proof, "
+                            "non-canonical scalar encodings (must accept) (uniform)",
+                 "status_matches_expectation": ok_status, "nullifiers_of_accepting_classes_match": ok_nul5 and ok_nul6,
+                 "accepted": int((st_m == 0).sum().item()),
                  "rejected_by_status": {str(k): int((st_m == k).sum().item()) for k in (6, 7, 0x81)},
-                 "replays_flagged_by_screen": replays, "replays_planted_valid": int(((expect[i4] == 0) & (expect[i4 - 1] == 0)).sum().item())}
+                 "replays_flagged_by_screen": replays, "replay_flags_equal_sort_based_reference": ok_flags,
+                 "second_spends_planted": m5, "exact_replays_planted": int(i4.numel())}
         assert ok_status, "mixed batch: a status differs from the class's expected status"
+        assert ok_nul5 and ok_nul6, "mixed batch: nullifier of an accepted tampered class differs"
+        assert ok_flags, "mixed batch: replay screen differs from the sort-based formulation"
         pv[tidx] = saved
-        del saved, st_m, d_flag, expect
+        del saved, st_m, d_flag, expect, flag_ref, k6
         torch.cuda.synchronize()
 
     # ---- e2e: pinned host buffers through the public C ABI (H2D + kernels + D2H inside the timed region) ----

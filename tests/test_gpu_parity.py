@@ -374,6 +374,25 @@ def test_client_generators_on_gpu(act, engine, octx):
     assert (vst[:64] == 7).all()
 
 
+def test_same_token_spent_twice_with_different_proofs(engine, octx):
+    """BASELINE config #5's "same-k different-proof replay": two honest proofs from ONE token (different charge and
+    randomness) both verify -- refund() cannot know (src/lib.rs:741-745) -- and carry the same nullifier; the batch replay
+    screen flags the later one.  Outputs equal the oracle's."""
+    n = 6
+    base = corpus.gen_valid(octx, n, seed=b"double-spend", threads=4)
+    st = corpus.trip_streams(b"double-spend", n)
+    tokens = corpus.tokens_from(base, st["pre"])
+    ones = np.frombuffer(b"".join((1).to_bytes(32, "little") for _ in range(n)), np.uint8)
+    p2, _, s2 = engine.batch_prove_spend(tokens, ones, seed=corpus.xof(b"second-proof", 32))
+    assert (s2 == 0).all() and (p2 != base["proofs"]).any()
+    both = np.concatenate([base["proofs"], p2]); rnd = np.frombuffer(corpus.xof(b"double-spend/rnd", 128 * 2 * n), np.uint8)
+    ref, nul, vst = engine.batch_verify_spend_and_refund(both, rnd)
+    o_ref, o_nul, o_st, _ = octx.batch_refund(both, rnd, threads=4)
+    assert (vst == 0).all() and (o_st == 0).all() and (ref == o_ref).all() and (nul == o_nul).all()
+    assert (nul[:32 * n] == nul[32 * n:]).all()
+    assert engine.flag_replays(vst, nul).tolist() == [0] * n + [3] * n
+
+
 def test_token_lifecycles_match_the_oracle(engine, octx):
     """Multi-generation token chains (corpus.LIFECYCLES: the reference's scenario tests, src/tests.rs:210-426,642-689,
     876-1059) through the C ABI: request, issue, issuance_check, prove_spend, verify+refund, refund_check generation
