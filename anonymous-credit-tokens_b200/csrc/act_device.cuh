@@ -185,7 +185,7 @@ ACT_FN ge fb_accumulate(ge acc, const fb_tab& T, const sc& s, bool negate) {
             const ge_niels* nxt = T.p + (size_t)(i + 1) * T.ent + (u32)(d < 0 ? -d : d);
             prefetch_line(nxt); prefetch_line(reinterpret_cast<const u8*>(nxt) + 95);
         }
-        acc = ge_add_niels_n(acc, load_niels(cur), neg);
+        acc = ge_add_niels_n<true>(acc, load_niels(cur), neg);    // public scalars: the variable-time add/sub forms
     }
     return acc;
 }
@@ -273,14 +273,14 @@ ACT_FN ge vb_mul(const vb_table* t, const sc& s, bool negate) { return vb_mul_mu
 // each scalar costs only 256/M doublings:  s*P = sum_k 2^(256k/M) * (sum_i 16^i d_{k*WIN+i}) P.
 // M = 4: 192 + 2*64 doublings instead of 2*256.  The tables are built once, then each scalar is processed on its own
 // (one accumulator live at a time: fewer registers, 4 resident blocks per SM).
-template <int M>
+template <int M, bool VT = false>
 ACT_FN void vb_split_tables(const ge& P, vb_table* t) {
     const int WIN = 64 / M;
     ge Q = P;
     ACT_NOUNROLL for (int k = 0; k < M; k++) {
         vb_table_build(&t[k], Q);
         if (k < M - 1) {
-            ACT_NOUNROLL for (int d = 0; d < 4 * WIN; d++) Q = ge_dbl_u(Q, d == 4 * WIN - 1);
+            ACT_NOUNROLL for (int d = 0; d < 4 * WIN; d++) Q = ge_dbl_u<VT>(Q, d == 4 * WIN - 1);
         }
     }
 }
@@ -299,7 +299,7 @@ ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
                     prefetch_line(&t[0].e[d0 < 0 ? -d0 : d0]);
                 }
 #endif
-                a = ge_dbl_u(a, d == 3);
+                a = ge_dbl_u<true>(a, d == 3);
             }
         }
         ACT_NOUNROLL for (int k = 0; k < M; k++) {
@@ -309,7 +309,7 @@ ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
             }
             // the doubling that follows the last addition of a window does not read T (the very last window's does: T goes on)
             int dk = sc_digit<4>(b, k * WIN + i);
-            a = ge_add_cached_u(a, tab_load(&t[k], (u32)(dk < 0 ? -dk : dk)), dk < 0 ? 0u : 1u, k + 1 < M || i == 0);   // -|d| * sign
+            a = ge_add_cached_u<true>(a, tab_load(&t[k], (u32)(dk < 0 ? -dk : dk)), dk < 0 ? 0u : 1u, k + 1 < M || i == 0);   // -|d| * sign
         }
     }
     return a;
@@ -569,7 +569,7 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
     }
     // Every scalar is HALVED: this stage produces C'/2 and the encode stage emits encode(2 * C'/2) with one batched
     // inversion per 16 points instead of one inverse square root per point.
-    vb_split_tables<ACT_RANGE_SPLIT>(P, tabs);
+    vb_split_tables<ACT_RANGE_SPLIT, true>(P, tabs);   // com_j is public
     u32* cp = cpts + ((size_t)2 * ACT_L * p + 2 * j) * 32;
     ACT_NOUNROLL for (int b = 0; b < 2; b++) {
         // b = 0: C'_j0 = [h2*w00 +] h3*z_j0 - com_j*gamma0_j                                 (:806-807,814-815)

@@ -283,6 +283,23 @@ __global__ void selftest_kernel(u32* fail) {
         hi2.v[7] = 0x7fffffffu; for (int i = 0; i < 7; i++) hi2.v[i] = 0xffffffffu - (u32)(it * i);   // just below 2^255
         if (!fe_eq(fe_add_tt(hi1, hi2), fe_add(hi1, hi2)) || !fe_eq(fe_add_tt(hi1, hi1), fe_add(hi1, hi1))) bad |= 1024;
         if (!fe_eq(fe_dbl_tt(hi1), fe_add(hi1, hi1)) || !fe_eq(fe_dbl_tt(hi2), fe_add(hi2, hi2))) bad |= 2048;
+        // the variable-time add / sub forms (public data) equal the two-pass forms word for word: on random operands and on
+        // operands that take the out-of-line branch (single ripple, and the ripple that wraps a second time)
+        {
+            fe x[6], y[6];
+            x[0] = a; y[0] = b;
+            for (int i = 0; i < 8; i++) { x[1].v[i] = 0xffffffffu; y[1].v[i] = b.v[i]; }
+            y[1].v[0] = 0xfffffff0u - (u32)(it & 7);                                      // sum wraps, low word lands within 38 of 2^32
+            x[2] = x[1]; for (int i = 0; i < 8; i++) y[2].v[i] = 0xffffffffu; y[2].v[0] = 0xfffffff0u + (u32)(it & 7);   // ... and ripples to the top
+            x[3] = fe_zero(); x[3].v[0] = 5u + (u32)(it & 7); for (int i = 0; i < 8; i++) y[3].v[i] = 0xffffffffu;      // difference borrows twice
+            x[4] = a; x[4].v[0] = (u32)(it & 31); x[4].v[7] &= 0x7fffffffu; y[4] = fe_zero(); y[4].v[7] = 0x80000000u | b.v[7];   // one borrow, low word below 38
+            x[5] = fe_zero(); y[5] = fe_zero(); y[5].v[0] = 1u + (u32)(it & 1);           // 0 - 1, 0 - 2
+            for (int k = 0; k < 6; k++) {
+                fe s1 = fe_add_v(x[k], y[k]), s2 = fe_add(x[k], y[k]), d1 = fe_sub_v(x[k], y[k]), d2 = fe_sub(x[k], y[k]);
+                fe e1 = fe_sub_v(y[k], x[k]), e2 = fe_sub(y[k], x[k]);
+                for (int i = 0; i < 8; i++) if (s1.v[i] != s2.v[i] || d1.v[i] != d2.v[i] || e1.v[i] != e2.v[i]) bad |= 4096;
+            }
+        }
     }
     // basepoint encodes to the RFC 9496 generator
     {

@@ -171,6 +171,93 @@ ACT_FN fe fe_sub(const fe& a, const fe& b) {
 }
 ACT_FN fe fe_neg(const fe& a) { return fe_sub(fe_zero(), a); }
 
+// ---- add / sub for PUBLIC data (ACT_RARE) ------------------------------------------------------------------
+// The second carry pass of fe_add / fe_sub only matters when folding the wrapped 2^256 (+-38) carries (borrows) out of the
+// LOW word, i.e. when the low word is within 38 of 2^32 (of 0): about 1 in 10^8 operations.  fe_add_v / fe_sub_v apply the
+// fold to the low word and call an out-of-line ripple in that case: 5-6 instructions fewer on the common path (the check and
+// the reconvergence pair cost 4), same result bit for bit; +1.5 % in the range kernel (profiles/r01k_variants_rare_branch.txt).
+// The branch depends on the data, so these forms are for public values only (range-proof commitments, fixed-base walks over
+// public scalars); everything that touches the key keeps the branch-free fe_add / fe_sub.
+#ifndef ACT_RARE
+#define ACT_RARE 1
+#endif
+#if ACT_PTX && ACT_RARE
+ACT_NOINLINE fe fe_ripple_up_(fe r) {        // + 2^32, and the fold of a second wrap (then the low word is below 38)
+    u32 c;
+    asm("add.cc.u32 %0, %0, 1;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.u32 %7, 0, 0;"
+        : "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c));
+    r.v[0] += c * 38u;
+    return r;
+}
+ACT_NOINLINE fe fe_ripple_down_(fe r) {      // - 2^32, and the fold of a second wrap (then the low word is above 2^32 - 39)
+    u32 c;
+    asm("sub.cc.u32 %0, %0, 1;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t"
+        "subc.cc.u32 %5, %5, 0;\n\t"
+        "subc.cc.u32 %6, %6, 0;\n\t"
+        "subc.u32 %7, 0, 0;"
+        : "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c));
+    r.v[0] -= c & 38u;
+    return r;
+}
+ACT_FN fe fe_add_v(const fe& a, const fe& b) {
+    fe r;
+    u32 c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    u32 f = (0u - c) & 38u;
+    r.v[0] += f;
+    if (r.v[0] < f) r = fe_ripple_up_(r);
+    return r;
+}
+ACT_FN fe fe_sub_v(const fe& a, const fe& b) {
+    fe r;
+    u32 c;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    u32 f = c & 38u;  // c is 0 or 0xffffffff
+    u32 lo = r.v[0];
+    r.v[0] = lo - f;
+    if (lo < f) r = fe_ripple_down_(r);
+    return r;
+}
+#else
+ACT_FN fe fe_add_v(const fe& a, const fe& b) { return fe_add(a, b); }
+ACT_FN fe fe_sub_v(const fe& a, const fe& b) { return fe_sub(a, b); }
+#endif
+template <bool VT> ACT_FN fe fe_add_x(const fe& a, const fe& b) { return VT ? fe_add_v(a, b) : fe_add(a, b); }
+template <bool VT> ACT_FN fe fe_sub_x(const fe& a, const fe& b) { return VT ? fe_sub_v(a, b) : fe_sub(a, b); }
+
 // ---- sums of PRODUCTS -----------------------------------------------------------------------------
 // "tight" = below 2^255 + 2^11, which is what fe_mul / fe_sq return under ACT_TIGHT (fe_fold9).  The sum of two tight values
 // is below 2^256 + 2^12: if it wraps, what is left is below 2^12, so the 38 that the lost 2^256 is worth goes onto the low word

@@ -90,16 +90,17 @@ ACT_GE_FN ge ge_add_cached(ge p, ge_cached q) {
 // the addition of the window loops: r = p + (neg ? -q : q) with a run-time (warp-uniform) choice of producing T -- a doubling
 // (which does not read T) follows the last addition of every window: 7M instead of 8M there.  The negation of q is folded
 // in: -q swaps q's Y+X / Y-X and flips the sign of the T term, which swaps G and F (no field negation needed).
+template <bool VT = false>   // VT: public data, the variable-time add / sub forms (fe_add_v, fe_sub_v)
 ACT_FN ge ge_add_cached_u(const ge& p, const ge_cached& q, u32 neg, bool want_t) {
     u32 zc_ = act_zero(); (void)zc_;
     // (statement and operand order chosen by the marshalling moves ptxas needs in the range kernel: 363 vs 381 instructions)
     fe TT = GE_MUL(p.T, q.T2d);
     fe ZZ = GE_MUL(p.Z, q.Z);
     fe ZZ2 = fe_dbl_tt(ZZ);                              // ZZ, PP, MM are products: tight
-    fe G0 = fe_add(ZZ2, TT), F0 = fe_sub(ZZ2, TT);
-    fe PP = GE_MUL(fe_select(q.YpX, q.YmX, neg), fe_add(p.Y, p.X));
-    fe MM = GE_MUL(fe_select(q.YmX, q.YpX, neg), fe_sub(p.Y, p.X));
-    fe E = fe_sub(PP, MM), H = fe_add_tt(PP, MM);
+    fe G0 = fe_add_x<VT>(ZZ2, TT), F0 = fe_sub_x<VT>(ZZ2, TT);
+    fe PP = GE_MUL(fe_select(q.YpX, q.YmX, neg), fe_add_x<VT>(p.Y, p.X));
+    fe MM = GE_MUL(fe_select(q.YmX, q.YpX, neg), fe_sub_x<VT>(p.Y, p.X));
+    fe E = fe_sub_x<VT>(PP, MM), H = fe_add_tt(PP, MM);
     fe G = fe_select(G0, F0, neg), F = fe_select(F0, G0, neg);
     ge r;
     r.X = GE_MUL(E, F); r.Z = GE_MUL(G, F); r.Y = GE_MUL(H, G);     // order chosen by the moves ptxas needs (369 vs 381 instructions)
@@ -121,14 +122,15 @@ ACT_GE_FN ge ge_add_niels(ge p, ge_niels q) {
     return r;
 }
 // r = p + (neg ? -q : q) for an affine-Niels table entry, the negation folded in as in ge_add_cached_u (public data)
+template <bool VT = false>
 ACT_FN ge ge_add_niels_n(const ge& p, const ge_niels& q, u32 neg) {
     u32 zc_ = act_zero(); (void)zc_;
-    fe PP = GE_MUL(fe_add(p.Y, p.X), fe_select(q.ypx, q.ymx, neg));
-    fe MM = GE_MUL(fe_sub(p.Y, p.X), fe_select(q.ymx, q.ypx, neg));
-    fe E = fe_sub(PP, MM), H = fe_add_tt(PP, MM);      // PP, MM are products: tight
+    fe PP = GE_MUL(fe_add_x<VT>(p.Y, p.X), fe_select(q.ypx, q.ymx, neg));
+    fe MM = GE_MUL(fe_sub_x<VT>(p.Y, p.X), fe_select(q.ymx, q.ypx, neg));
+    fe E = fe_sub_x<VT>(PP, MM), H = fe_add_tt(PP, MM);      // PP, MM are products: tight
     fe TT = GE_MUL(p.T, q.xy2d);
-    fe ZZ2 = fe_add(p.Z, p.Z);
-    fe G0 = fe_add(ZZ2, TT), F0 = fe_sub(ZZ2, TT);
+    fe ZZ2 = fe_add_x<VT>(p.Z, p.Z);
+    fe G0 = fe_add_x<VT>(ZZ2, TT), F0 = fe_sub_x<VT>(ZZ2, TT);
     fe G = fe_select(G0, F0, neg), F = fe_select(F0, G0, neg);
     ge r;
     r.X = GE_MUL(E, F); r.Y = GE_MUL(H, G); r.Z = GE_MUL(G, F); r.T = GE_MUL(E, H);
@@ -167,15 +169,16 @@ ACT_FN ge ge_dbl(const ge& p, bool want_t) { return want_t ? ge_dbl_t(p) : ge_db
 // doubling with a run-time (warp-uniform) choice of producing T: one instance of the code serves both forms, which
 // keeps the window loops small.  (Inlining the field multiplications into the point operations was measured on
 // B200: the 17-37 KB loop bodies miss the instruction cache and run 7-25 % slower than the call form, see DESIGN.md.)
+template <bool VT = false>
 ACT_FN ge ge_dbl_u(const ge& p, bool want_t) {
     u32 zc_ = act_zero(); (void)zc_;
     fe XX = GE_SQ(p.X), YY = GE_SQ(p.Y);
-    fe Yc = fe_add_tt(YY, XX), Zc = fe_sub(YY, XX);     // XX, YY, ZZ are products: tight
+    fe Yc = fe_add_tt(YY, XX), Zc = fe_sub_x<VT>(YY, XX);     // XX, YY, ZZ are products: tight
     fe ZZ = GE_SQ(p.Z);
     fe ZZ2 = fe_dbl_tt(ZZ);
-    fe Tc = fe_sub(ZZ2, Zc);
-    fe XpY2 = GE_SQ(fe_add(p.X, p.Y));
-    fe Xc = fe_sub(XpY2, Yc);
+    fe Tc = fe_sub_x<VT>(ZZ2, Zc);
+    fe XpY2 = GE_SQ(fe_add_x<VT>(p.X, p.Y));
+    fe Xc = fe_sub_x<VT>(XpY2, Yc);
     ge r;
     // (call and operand order chosen by the marshalling moves ptxas needs for them in the range kernel: 262 vs 272 instructions)
     r.Y = GE_MUL(Yc, Zc); r.Z = GE_MUL(Tc, Zc); r.X = GE_MUL(Tc, Xc);
