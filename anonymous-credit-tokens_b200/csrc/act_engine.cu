@@ -299,6 +299,19 @@ __global__ void selftest_kernel(u32* fail) {
                 fe e1 = fe_sub_v(y[k], x[k]), e2 = fe_sub(y[k], x[k]);
                 for (int i = 0; i < 8; i++) if (s1.v[i] != s2.v[i] || d1.v[i] != d2.v[i] || e1.v[i] != e2.v[i]) bad |= 4096;
             }
+            // the point operations instantiated for public data equal the branch-free instances on the same (arbitrary) coordinates,
+            // with operands that make their first sums / differences take the rare paths in either order
+            for (int k = 0; k < 12; k++) {
+                ge P; P.X = (k & 1) ? y[k >> 1] : x[k >> 1]; P.Y = (k & 1) ? x[k >> 1] : y[k >> 1]; P.Z = a; P.T = b;
+                ge_cached Q; Q.YpX = b; Q.YmX = a; Q.Z = x[0]; Q.T2d = y[4];
+                ge_niels N; N.ypx = a; N.ymx = y[4]; N.xy2d = b;
+                ge r1 = ge_dbl_u<true>(P, true), r2 = ge_dbl_u<false>(P, true);
+                ge r3 = ge_add_cached_u<true>(P, Q, (u32)(k & 1), true), r4 = ge_add_cached_u<false>(P, Q, (u32)(k & 1), true);
+                ge r5 = ge_add_niels_n<true>(P, N, (u32)(k & 1)), r6 = ge_add_niels_n<false>(P, N, (u32)(k & 1));
+                if (!(fe_eq(r1.X, r2.X) & fe_eq(r1.Y, r2.Y) & fe_eq(r1.Z, r2.Z) & fe_eq(r1.T, r2.T))) bad |= 8192;
+                if (!(fe_eq(r3.X, r4.X) & fe_eq(r3.Y, r4.Y) & fe_eq(r3.Z, r4.Z) & fe_eq(r3.T, r4.T))) bad |= 8192;
+                if (!(fe_eq(r5.X, r6.X) & fe_eq(r5.Y, r6.Y) & fe_eq(r5.Z, r6.Z) & fe_eq(r5.T, r6.T))) bad |= 8192;
+            }
         }
     }
     // basepoint encodes to the RFC 9496 generator
