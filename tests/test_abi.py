@@ -99,3 +99,59 @@ def test_cbor_pack_roundtrip_and_lenient_rules(act):
     assert st.tolist() == [0] and rec.tobytes().hex() == g["refund"]
     rec, st = act.pack_issuance_responses_cbor([bytes.fromhex(g["cbor_response"])])
     assert st.tolist() == [0] and rec.tobytes().hex() == g["response"]
+
+
+def test_cbor_pack_survives_mutated_and_truncated_input(act):
+    """No input may crash the host parser or write outside its record (the reference never panics on adversarial bytes,
+    SURVEY 8b): byte flips, truncations and random garbage give 0 / 0x82 / 0x83, a record accepted with 0 re-encodes to a
+    canonical item that unpacks to the same record, and rejected items leave a zero record."""
+    g = _golden()
+    rs = np.random.RandomState(2026)
+    proof = bytes.fromhex(g["proof"])
+    kinds = [
+        (act.encode_spend_proof_cbor(proof), act.pack_spend_proofs_cbor, act.encode_spend_proof_cbor, 16832, 300),
+        (bytes.fromhex(g["cbor_request"]), act.pack_issuance_requests_cbor, act.encode_issuance_request_cbor, 128, 1500),
+        (bytes.fromhex(g["cbor_response"]), act.pack_issuance_responses_cbor, act.encode_issuance_response_cbor, 160, 1500),
+        (bytes.fromhex(g["cbor_refund"]), act.pack_refunds_cbor, act.encode_refund_cbor, 128, 1500),
+    ]
+    for enc, pack, encode, rec_bytes, cases in kinds:
+        items = []
+        for c in range(cases):
+            b = bytearray(enc)
+            mode = c % 4
+            if mode == 0:                       # flip 1-3 bytes, biased to the structural bytes at the front
+                for _ in range(1 + rs.randint(3)):
+                    pos = rs.randint(min(len(b), 64)) if rs.rand() < 0.5 else rs.randint(len(b))
+                    b[pos] ^= 1 << rs.randint(8)
+            elif mode == 1:                     # truncate
+                b = b[:rs.randint(len(b))]
+            elif mode == 2:                     # overwrite a run with random bytes
+                pos = rs.randint(len(b)); ln = 1 + rs.randint(40)
+                b[pos:pos + ln] = rs.randint(0, 256, size=ln, dtype=np.uint8).tobytes()
+            else:                               # garbage of a similar length, sometimes with a plausible map header
+                b = bytearray(rs.randint(0, 256, size=rs.randint(1, len(enc) + 8), dtype=np.uint8).tobytes())
+                if rs.rand() < 0.5:
+                    b[0] = enc[0]
+            items.append(bytes(b))
+        rec, st = pack(items)
+        rec = rec.reshape(cases, rec_bytes)
+        assert set(np.unique(st)) <= {0, 0x82, 0x83}
+        assert (st != 0).sum() > cases // 4 and (st == 0).sum() > 0
+        assert not rec[st != 0].any()
+        ok = np.nonzero(st == 0)[0]
+        # differential check with an independent decoder: whenever cbor2 reads the same item as a map, the accepted record holds
+        # exactly the map's fields (flat messages; the last duplicate wins in both)
+        if rec_bytes != 16832:
+            import cbor2
+            checked = 0
+            for i in ok:
+                try:
+                    d = cbor2.loads(items[i])
+                except Exception:
+                    continue
+                if isinstance(d, dict) and all(isinstance(d.get(k), bytes) and len(d[k]) == 32 for k in range(1, rec_bytes // 32 + 1)):
+                    assert b"".join(d[k] for k in range(1, rec_bytes // 32 + 1)) == rec[i].tobytes()
+                    checked += 1
+            assert checked > 0
+        again, st2 = pack([encode(rec[i]) for i in ok])
+        assert (st2 == 0).all() and (again.reshape(len(ok), rec_bytes) == rec[ok]).all()
