@@ -257,3 +257,31 @@ def test_token_lifecycles_match_the_oracle(octx):
         prove_spend = staticmethod(lambda tokens, charges, rnd: hs.prove_spend(tokens, charges, rnd=rnd))
 
     assert corpus.run_lifecycles(Impl) == corpus.run_lifecycles(corpus.OracleImpl(octx))
+
+
+def test_cbor_skeleton_check_is_exact_at_every_byte(act):
+    """Fast-path contract (act_aux.cuh, host build): a one-bit change at ANY structural byte of a canonical item makes the
+    skeleton check hand the item back (0xFF); a change inside a payload is still canonical, and then the record equals what
+    the lenient host parser (the reference's from_cbor semantics) extracts from the same bytes."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trip.json")))
+    recs = {0: bytes.fromhex(g["request"]), 1: bytes.fromhex(g["response"]), 2: bytes.fromhex(g["proof"]), 3: bytes.fromhex(g["refund"])}
+    enc = {0: act.encode_issuance_request_cbor, 1: act.encode_issuance_response_cbor, 2: act.encode_spend_proof_cbor, 3: act.encode_refund_cbor}
+    pack = {0: act.pack_issuance_requests_cbor, 1: act.pack_issuance_responses_cbor, 2: act.pack_spend_proofs_cbor, 3: act.pack_refunds_cbor}
+    rs = np.random.RandomState(5)
+    for kind, rec in recs.items():
+        nrec = act.RECORD_BYTES[kind]
+        lo, hi = enc[kind](bytes(nrec)), enc[kind](b"\xff" * nrec)
+        payload = np.frombuffer(lo, np.uint8) != np.frombuffer(hi, np.uint8)
+        assert payload.sum() == nrec
+        item = enc[kind](rec)
+        positions = range(len(item)) if kind != 2 else sorted(set(np.nonzero(~payload)[0].tolist()) | set(rs.randint(0, len(item), 400).tolist()))
+        accepted = []
+        for pos in positions:
+            b = bytearray(item); b[pos] ^= 1 << rs.randint(8)
+            back, st = HS.cbor_skeleton_unpack(kind, bytes(b), nrec)
+            assert st == (0 if payload[pos] else 0xFF), (kind, pos)
+            if st == 0:
+                accepted.append((bytes(b), back))
+        host_rec, host_st = pack[kind]([a for a, _ in accepted])
+        assert (host_st == 0).all() and host_rec.tobytes() == b"".join(r for _, r in accepted)
