@@ -314,6 +314,62 @@ ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
     }
     return a;
 }
+// ---- EXPERIMENTAL, off by default, NOT yet measured on the GPU (ACT_RANGE_BUCKETS=1) ------------------
+// Right-to-left evaluation of the range-proof pair: the two results -s0*P and -s1*P share ALL doublings.  Q_i = 16^i P is
+// formed once (252 doublings instead of 192 + 2 x 60); each result collects -sign(d_i) Q_i into the bucket of |d_i| (9 buckets
+// per result, bucket 0 absorbs the zero digits so that every lane adds at every step) and sum_d d * bucket_d closes it
+// (running sums, 14 additions).  Buckets live in the thread's table scratch (18 of its 36 entries), extended coordinates.
+// Same group elements as vb_mul_split_neg, so the encoded commitments are identical (tests/test_hostsim.py builds this form too).
+#ifndef ACT_RANGE_BUCKETS
+#define ACT_RANGE_BUCKETS 0
+#endif
+#if ACT_RANGE_BUCKETS
+ACT_FN u32* bucket_ptr(vb_table* t, u32 idx) { return reinterpret_cast<u32*>(&t[idx / 9].e[idx % 9]); }
+ACT_FN void bucket_store(vb_table* t, u32 idx, const ge& p) {
+    u32* q = bucket_ptr(t, idx);
+    store8(q, p.X.v); store8(q + 8, p.Y.v); store8(q + 16, p.Z.v); store8(q + 24, p.T.v);
+}
+ACT_FN ge bucket_load(vb_table* t, u32 idx) {
+    ge p;
+    const u32* q = bucket_ptr(t, idx);
+    load8_rw(p.X.v, q); load8_rw(p.Y.v, q + 8); load8_rw(p.Z.v, q + 16); load8_rw(p.T.v, q + 24);
+    return p;
+}
+ACT_FN void vb_pair_buckets_fill(const ge& P, const sc& s0, const sc& s1, vb_table* t) {
+    sc b0 = sc_bias<4>(s0), b1 = sc_bias<4>(s1);
+    {
+        ge id = ge_identity();
+        ACT_NOUNROLL for (u32 k = 0; k < 18; k++) bucket_store(t, k, id);
+    }
+    ge Q = P;
+    ACT_NOUNROLL for (int i = 0; i < 64; i++) {
+        ge_cached Qc = ge_to_cached(Q);
+        ACT_NOUNROLL for (int r = 0; r < 2; r++) {
+            int d = sc_digit<4>(r ? b1 : b0, i);
+            u32 idx = 9u * (u32)r + (u32)(d < 0 ? -d : d);
+            if (i + 1 < 64 || r == 0) {   // the bucket of the next addition travels to L1 while this one runs
+                int dn = r ? sc_digit<4>(b0, i + 1) : sc_digit<4>(b1, i);
+                prefetch_line(bucket_ptr(t, 9u * (u32)(r ^ 1) + (u32)(dn < 0 ? -dn : dn)));
+            }
+            ge B = bucket_load(t, idx);
+            B = ge_add_cached_u<true>(B, Qc, d < 0 ? 0u : 1u, true);      // bucket += -sign(d) Q_i
+            bucket_store(t, idx, B);
+        }
+        if (i + 1 < 64) {
+            ACT_NOUNROLL for (int k = 0; k < 4; k++) Q = ge_dbl_u<true>(Q, k == 3);
+        }
+    }
+}
+ACT_FN ge vb_pair_buckets_sum(vb_table* t, int r) {
+    ge S = bucket_load(t, 9u * (u32)r + 8u), R = S;
+    ACT_NOUNROLL for (u32 d = 7; d >= 1; d--) {
+        S = ge_add_cached(S, ge_to_cached(bucket_load(t, 9u * (u32)r + d)));
+        R = ge_add_cached(R, ge_to_cached(S));
+    }
+    return R;
+}
+#endif
+
 // s * P for a secret s
 ACT_NOINLINE void vb_mul_ct_(ge* out, const ge* P, const sc* s) {
     vb_table t;
@@ -569,7 +625,15 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
     }
     // Every scalar is HALVED: this stage produces C'/2 and the encode stage emits encode(2 * C'/2) with one batched
     // inversion per 16 points instead of one inverse square root per point.
+#if ACT_RANGE_BUCKETS
+    {
+        sc g0 = load_scalar(pf + 8 * (140 + j));
+        sc g1 = sc_sub(load_scalar(pf + 8 * 132), g0);
+        vb_pair_buckets_fill(P, sc_half(g0), sc_half(g1), tabs);
+    }
+#else
     vb_split_tables<ACT_RANGE_SPLIT, true>(P, tabs);   // com_j is public
+#endif
     u32* cp = cpts + ((size_t)2 * ACT_L * p + 2 * j) * 32;
     ACT_NOUNROLL for (int b = 0; b < 2; b++) {
         // b = 0: C'_j0 = [h2*w00 +] h3*z_j0 - com_j*gamma0_j                                 (:806-807,814-815)
@@ -577,10 +641,14 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
         //        [..] for j = 0 only, added by spend_head_thread
         //        (the reference's base com_j - H1 is never formed: -(com_j - h1)*g = h1*g - com_j*g)
         // Scalars are re-derived from the proof bytes where they are used: nothing but the accumulator stays live.
+#if ACT_RANGE_BUCKETS
+        ge Q = vb_pair_buckets_sum(tabs, b);
+#else
         sc gb = load_scalar(pf + 8 * (140 + j));
         if (b) gb = sc_sub(load_scalar(pf + 8 * 132), gb);                                  // gamma01[j] (:801,811)
         gb = sc_half(gb);
         ge Q = vb_mul_split_neg<ACT_RANGE_SPLIT>(tabs, gb);
+#endif
         // (the h2 terms exist for j = 0 only: one lane of one warp in four would run 40 additions alone, so stage 2 -- a thread
         // per proof -- adds them to the stored halves instead, spend_head_thread)
         ACT_NOUNROLL for (int t = 0; t < 2; t++) {
