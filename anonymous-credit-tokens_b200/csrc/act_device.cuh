@@ -363,8 +363,8 @@ ACT_FN void vb_pair_buckets_fill(const ge& P, const sc& s0, const sc& s1, vb_tab
 ACT_FN ge vb_pair_buckets_sum(vb_table* t, int r) {
     ge S = bucket_load(t, 9u * (u32)r + 8u), R = S;
     ACT_NOUNROLL for (u32 d = 7; d >= 1; d--) {
-        S = ge_add_cached(S, ge_to_cached(bucket_load(t, 9u * (u32)r + d)));
-        R = ge_add_cached(R, ge_to_cached(S));
+        S = ge_add_cached_u<true>(S, ge_to_cached(bucket_load(t, 9u * (u32)r + d)), 0u, true);
+        R = ge_add_cached_u<true>(R, ge_to_cached(S), 0u, true);
     }
     return R;
 }
