@@ -319,7 +319,7 @@ ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
 // formed once (252 doublings instead of 192 + 2 x 60); each result collects -sign(d_i) Q_i into the bucket of |d_i| (9 buckets
 // per result, bucket 0 absorbs the zero digits so that every lane adds at every step) and sum_d d * bucket_d closes it
 // (running sums, 14 additions).  Buckets live in the thread's table scratch (18 of its 36 entries), extended coordinates.
-// Same group elements as vb_mul_split_neg, so the encoded commitments are identical (tests/test_hostsim.py builds this form too).
+// Same group elements as vb_mul_split_neg, so the encoded commitments are identical (tests/hostsim builds this form too).
 #ifndef ACT_RANGE_BUCKETS
 #define ACT_RANGE_BUCKETS 0
 #endif
