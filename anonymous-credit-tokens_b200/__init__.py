@@ -70,7 +70,10 @@ EXPORTED_SYMBOLS = [
     "act_encode_spend_proof_cbor", "act_encode_refund_cbor",
     "act_flag_replays", "act_flag_replays_dev", "act_unpack_cbor", "act_unpack_cbor_dev", "act_encode_cbor", "act_encode_cbor_dev",
     "act_batch_request", "act_batch_request_dev", "act_batch_prove_spend", "act_batch_prove_spend_dev",
-    "act_batch_issue_seq", "act_batch_verify_spend_and_refund_seq",
+    "act_batch_issue_seq", "act_batch_verify_spend_and_refund_seq", "act_engine_set_spend_chunk",
+    "act_engine_create_multi", "act_engine_replica_count", "act_engine_replica",
+    "act_batch_issue_verify", "act_batch_issue_sign", "act_batch_spend_verify", "act_batch_refund_sign",
+    "act_batch_verify_spend_and_refund_screened",
 ]
 
 
@@ -97,6 +100,7 @@ def load_library():
     lib.act_engine_create.argtypes = [C.POINTER(vp), i32, vp, vp, vp]; lib.act_engine_create.restype = i32
     lib.act_engine_destroy.argtypes = [vp]; lib.act_engine_destroy.restype = None
     lib.act_engine_device.argtypes = [vp]; lib.act_engine_device.restype = i32
+    lib.act_engine_set_spend_chunk.argtypes = [vp, sz]; lib.act_engine_set_spend_chunk.restype = i32
     lib.act_public_key.argtypes = [i32, vp, vp]; lib.act_public_key.restype = i32
     lib.act_host_alloc.argtypes = [sz]; lib.act_host_alloc.restype = vp
     lib.act_host_free.argtypes = [vp]; lib.act_host_free.restype = None
@@ -129,6 +133,14 @@ def load_library():
     lib.act_batch_prove_spend.argtypes = [vp, sz, vp, vp, vp, vp, u64, vp, vp, vp]; lib.act_batch_prove_spend.restype = i32
     lib.act_batch_issue_seq.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, vp]; lib.act_batch_issue_seq.restype = i32
     lib.act_batch_verify_spend_and_refund_seq.argtypes = [vp, sz, vp, vp, sz, vp, vp, vp, vp]; lib.act_batch_verify_spend_and_refund_seq.restype = i32
+    lib.act_engine_create_multi.argtypes = [C.POINTER(vp), vp, i32, vp, vp, vp]; lib.act_engine_create_multi.restype = i32
+    lib.act_engine_replica_count.argtypes = [vp]; lib.act_engine_replica_count.restype = i32
+    lib.act_engine_replica.argtypes = [vp, i32]; lib.act_engine_replica.restype = vp
+    lib.act_batch_issue_verify.argtypes = [vp, sz, vp, vp]; lib.act_batch_issue_verify.restype = i32
+    lib.act_batch_issue_sign.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp]; lib.act_batch_issue_sign.restype = i32
+    lib.act_batch_spend_verify.argtypes = [vp, sz, vp, vp, vp, vp]; lib.act_batch_spend_verify.restype = i32
+    lib.act_batch_refund_sign.argtypes = [vp, sz, vp, vp, vp, sz, vp]; lib.act_batch_refund_sign.restype = i32
+    lib.act_batch_verify_spend_and_refund_screened.argtypes = [vp, sz, vp, vp, sz, vp, vp, vp, vp]; lib.act_batch_verify_spend_and_refund_screened.restype = i32
     _lib = lib
     return lib
 
@@ -206,12 +218,24 @@ class PrivateKey:
 class Engine:
     """One (Params, PrivateKey) pair resident on one GPU; batch forms of the reference's issuer-side calls."""
 
-    def __init__(self, params, key, device=0):
+    def __init__(self, params, key, device=0, devices=None):
+        """device: one GPU; devices=[...]: a multi-device engine (act_engine_create_multi) whose host-buffer calls shard the
+        batch contiguously over one replica per listed GPU."""
         self.lib = load_library()
-        self.device = device
         self._h = C.c_void_p()
         hb, xb, wb = _u8(params.h, 96), _u8(key.x, 32), _u8(key.w, 32)
-        _check(self.lib.act_engine_create(C.byref(self._h), device, hb.ctypes.data, xb.ctypes.data, wb.ctypes.data), "act_engine_create")
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*devices)
+            self.device = devices[0]
+            _check(self.lib.act_engine_create_multi(C.byref(self._h), C.cast(devs, C.c_void_p), len(devices), hb.ctypes.data, xb.ctypes.data, wb.ctypes.data),
+                   "act_engine_create_multi")
+        else:
+            self.device = device
+            _check(self.lib.act_engine_create(C.byref(self._h), device, hb.ctypes.data, xb.ctypes.data, wb.ctypes.data), "act_engine_create")
+
+    @property
+    def replica_count(self):
+        return int(self.lib.act_engine_replica_count(self._h))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -233,6 +257,10 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.act_engine_launch_count(self._h))
+
+    def set_spend_chunk(self, proofs):
+        """Proofs per chunk of the spend pipeline (default 65536)."""
+        _check(self.lib.act_engine_set_spend_chunk(self._h, proofs), "act_engine_set_spend_chunk")
 
     def set_timing(self, enable=True):
         _check(self.lib.act_engine_set_timing(self._h, 1 if enable else 0), "act_engine_set_timing")
@@ -301,6 +329,55 @@ class Engine:
                                                               ref.ctypes.data, nul.ctypes.data, st.ctypes.data, C.addressof(used)),
                "act_batch_verify_spend_and_refund_seq")
         return ref, nul, st, int(used.value)
+
+    # ---- two-pass forms (verify, then sign with randomness for the accepted requests only) ----
+    def batch_issue_verify(self, requests):
+        req = _u8(requests); n = req.size // REQUEST_BYTES
+        st = np.zeros(n, np.uint8)
+        _check(self.lib.act_batch_issue_verify(self._h, n, req.ctypes.data, st.ctypes.data), "act_batch_issue_verify")
+        return st
+
+    def batch_issue_sign(self, requests, cs, status, rnd):
+        """rnd: 128 bytes per accepted request (status 0), in slice order."""
+        req = _u8(requests); n = req.size // REQUEST_BYTES
+        c, st, r = _u8(cs, n * 32, "cs"), _u8(status, n, "status"), _u8(rnd)
+        resp = np.zeros(n * RESPONSE_BYTES, np.uint8)
+        _check(self.lib.act_batch_issue_sign(self._h, n, req.ctypes.data, c.ctypes.data, st.ctypes.data, r.ctypes.data if r.size else None, r.size, resp.ctypes.data),
+               "act_batch_issue_sign")
+        return resp
+
+    def batch_spend_verify(self, proofs):
+        """-> (nullifiers n*32, status n, kprime n*128): the verification half of batch_verify_spend_and_refund."""
+        pf = _u8(proofs); n = pf.size // PROOF_BYTES
+        nul = np.zeros(n * 32, np.uint8); st = np.zeros(n, np.uint8); kp = np.zeros(n * 128, np.uint8)
+        _check(self.lib.act_batch_spend_verify(self._h, n, pf.ctypes.data, nul.ctypes.data, st.ctypes.data, kp.ctypes.data), "act_batch_spend_verify")
+        return nul, st, kp
+
+    def batch_refund_sign(self, kprime, status, rnd):
+        st = _u8(status); n = st.size
+        kp, r = _u8(kprime, n * 128, "kprime"), _u8(rnd)
+        ref = np.zeros(n * REFUND_BYTES, np.uint8)
+        _check(self.lib.act_batch_refund_sign(self._h, n, kp.ctypes.data, st.ctypes.data, r.ctypes.data if r.size else None, r.size, ref.ctypes.data),
+               "act_batch_refund_sign")
+        return ref
+
+    def batch_verify_spend_and_refund_screened(self, proofs, rnd, seen=None, out=None):
+        """verify + refund + replay screen (status 3 = DoubleSpendError, no refund) in one call; on a multi-device engine the
+        status + nullifier gather to replica 0 runs over NVLink.  Returns (refunds, nullifiers, status)."""
+        pf = _u8(proofs); n = pf.size // PROOF_BYTES
+        r = _u8(rnd, n * RND_BYTES, "rnd")
+        sn = _u8(seen) if seen is not None and len(seen) else np.zeros(0, np.uint8)
+        if out is None:
+            ref = np.zeros(n * REFUND_BYTES, np.uint8); nul = np.zeros(n * 32, np.uint8); st = np.zeros(n, np.uint8)
+        else:
+            ref, nul, st = out
+        _check(self.lib.act_batch_verify_spend_and_refund_screened(self._h, n, pf.ctypes.data, r.ctypes.data, sn.size // 32, sn.ctypes.data if sn.size else None,
+                                                                   ref.ctypes.data, nul.ctypes.data, st.ctypes.data), "act_batch_verify_spend_and_refund_screened")
+        return ref, nul, st
+
+    def batch_verify_spend_and_refund_screened_ptr(self, n, proofs, rnd, n_seen, seen, refunds, nullifiers, status):
+        _check(self.lib.act_batch_verify_spend_and_refund_screened(self._h, n, proofs, rnd, n_seen, seen, refunds, nullifiers, status),
+               "act_batch_verify_spend_and_refund_screened")
 
     # ---- client-side batch generators (fixture grade, not constant time) ----
     def batch_request(self, pre, rnd):

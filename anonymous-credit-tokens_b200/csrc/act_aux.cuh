@@ -89,19 +89,39 @@ __device__ __forceinline__ bool rp_equal(const uint4* a, const uint4* b) {
     uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
     return ((a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w)) == 0;
 }
-// keyed mix of all 32 bytes (nullifiers are chosen by clients: the seed keeps crafted collisions from piling up in one bucket)
-__device__ __forceinline__ u32 rp_hash(const uint4* k, u32 seed) {
-    uint4 a = k[0], b = k[1];
-    u32 h = seed;
-    u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+// Keyed PRF over all 32 bytes: SipHash-1-3 under a 128-bit key the engine draws from the OS CSPRNG at creation (tweaked per call).
+// Nullifiers are chosen by clients, so an unkeyed or predictable mix would let them aim many accepted proofs at one probe run
+// (quadratic probing work inside one launch); under a secret key the slots of distinct nullifiers are unpredictable, and equal
+// nullifiers never lengthen a run (they meet their own slot).
+struct rp_key128 { u64 k0, k1; };
+#define RP_ROTL(x, b) (((x) << (b)) | ((x) >> (64 - (b))))
+#define RP_SIPROUND                                                                             \
+    do {                                                                                        \
+        v0 += v1; v1 = RP_ROTL(v1, 13); v1 ^= v0; v0 = RP_ROTL(v0, 32);                         \
+        v2 += v3; v3 = RP_ROTL(v3, 16); v3 ^= v2;                                               \
+        v0 += v3; v3 = RP_ROTL(v3, 21); v3 ^= v0;                                               \
+        v2 += v1; v1 = RP_ROTL(v1, 17); v1 ^= v2; v2 = RP_ROTL(v2, 32);                         \
+    } while (0)
+__host__ __device__ __forceinline__ u64 rp_siphash13(const u64 m[4], rp_key128 key) {
+    u64 v0 = key.k0 ^ 0x736f6d6570736575ull, v1 = key.k1 ^ 0x646f72616e646f6dull;
+    u64 v2 = key.k0 ^ 0x6c7967656e657261ull, v3 = key.k1 ^ 0x7465646279746573ull;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { h ^= w[i]; h *= 0x9e3779b1u; h ^= h >> 15; }
-    h *= 0x85ebca6bu; h ^= h >> 13;
-    return h;
+    for (int i = 0; i < 4; i++) { v3 ^= m[i]; RP_SIPROUND; v0 ^= m[i]; }
+    const u64 last = (u64)32 << 56;   // length byte, no tail bytes
+    v3 ^= last; RP_SIPROUND; v0 ^= last;
+    v2 ^= 0xff;
+    RP_SIPROUND; RP_SIPROUND; RP_SIPROUND;
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+__device__ __forceinline__ u32 rp_hash(const uint4* k, rp_key128 key) {
+    uint4 a = k[0], b = k[1];
+    u64 m[4] = {(u64)a.x | ((u64)a.y << 32), (u64)a.z | ((u64)a.w << 32), (u64)b.x | ((u64)b.y << 32), (u64)b.z | ((u64)b.w << 32)};
+    u64 h = rp_siphash13(m, key);
+    return (u32)h ^ (u32)(h >> 32);
 }
 // insert pass: table[slot] = lowest id whose key hashes there.  ids 0..n_seen-1 are the caller's seen set (always "first").
 __global__ void __launch_bounds__(256) replay_insert_kernel(u32 n, u32 n_seen, const u8* __restrict__ status, const uint4* __restrict__ seen,
-                                                            const uint4* __restrict__ nul, u32* table, u32 mask, u32 seed) {
+                                                            const uint4* __restrict__ nul, u32* table, u32 mask, rp_key128 seed) {
     u32 id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n + n_seen) return;
     if (id >= n_seen && status[id - n_seen] != 0) return;   // only accepted proofs take part
@@ -119,7 +139,7 @@ __global__ void __launch_bounds__(256) replay_insert_kernel(u32 n, u32 n_seen, c
     }
 }
 __global__ void __launch_bounds__(256) replay_resolve_kernel(u32 n, u32 n_seen, const u8* __restrict__ status, const uint4* __restrict__ seen,
-                                                             const uint4* __restrict__ nul, const u32* __restrict__ table, u32 mask, u32 seed,
+                                                             const uint4* __restrict__ nul, const u32* __restrict__ table, u32 mask, rp_key128 seed,
                                                              u8* __restrict__ out) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -314,14 +314,15 @@ ACT_FN ge vb_mul_split_neg(const vb_table* t, const sc& s) {
     }
     return a;
 }
-// ---- EXPERIMENTAL, off by default, NOT yet measured on the GPU (ACT_RANGE_BUCKETS=1) ------------------
+// ---- the form the range kernel uses (ACT_RANGE_BUCKETS=1, the default since round 2: 215.5k vs 207.3k proofs/s in the kernel on
+// B200, profiles/r02a_variants_buckets.txt; ACT_RANGE_BUCKETS=0 keeps the window form above for A/B runs) ------------------
 // Right-to-left evaluation of the range-proof pair: the two results -s0*P and -s1*P share ALL doublings.  Q_i = 16^i P is
 // formed once (252 doublings instead of 192 + 2 x 60); each result collects -sign(d_i) Q_i into the bucket of |d_i| (9 buckets
 // per result, bucket 0 absorbs the zero digits so that every lane adds at every step) and sum_d d * bucket_d closes it
 // (running sums, 14 additions).  Buckets live in the thread's table scratch (18 of its 36 entries), extended coordinates.
 // Same group elements as vb_mul_split_neg, so the encoded commitments are identical (tests/hostsim builds this form too).
 #ifndef ACT_RANGE_BUCKETS
-#define ACT_RANGE_BUCKETS 0
+#define ACT_RANGE_BUCKETS 1
 #endif
 #if ACT_RANGE_BUCKETS
 ACT_FN u32* bucket_ptr(vb_table* t, u32 idx) { return reinterpret_cast<u32*>(&t[idx / 9].e[idx % 9]); }
@@ -467,6 +468,14 @@ ACT_NOINLINE void encode4_doubled_(u32* out /* 4 x 8 words */, const ge* pts /* 
         ACT_UNROLL for (int k = 0; k < 8; k++) out[8 * i + k] = w[k] & m;
     }
 }
+// Overwrites a secret-derived local object once it is dead.  The volatile stores cannot be elided, so whichever home the
+// compiler gave the object (registers or its local-memory slot) holds zeros afterwards; spill slots the compiler created on
+// its own are covered by scrub_local_kernel (act_engine.cu), which the engine runs when it is destroyed.
+template <typename T>
+ACT_FN void secret_wipe(T* obj) {
+    volatile u32* q = reinterpret_cast<volatile u32*>(obj);
+    ACT_UNROLL for (unsigned i = 0; i < sizeof(T) / 4; i++) q[i] = 0u;
+}
 // X_A given; rnd = 32 words (e_wide || alpha_wide).  kind = ACT_TR_RESPOND (c, e, points) or ACT_TR_REFUND (e, points).
 // Writes A (8 words), e, gamma, z.
 ACT_NOINLINE void bbs_sign_(const act_ctx* C, const ge* X_A, const u32* rnd, int kind, const sc* c,
@@ -496,6 +505,10 @@ ACT_NOINLINE void bbs_sign_(const act_ctx* C, const ge* X_A, const u32* rnd, int
     sc gamma = tr_challenge(&tr);
     *e_out = e; *gamma_out = gamma;
     *z_out = sc_add(sc_mul(gamma, ex), alpha);                   // z = gamma*(x+e) + alpha
+    // ZeroizeOnDrop parity (the reference zeroises its secret-bearing values, src/lib.rs:160,571,1160): everything derived from
+    // x or alpha that is not an output is overwritten before the thread leaves
+    secret_wipe(&ex); secret_wipe(&inv); secret_wipe(&alpha); secret_wipe(&ainv); secret_wipe(&ah);
+    secret_wipe(&P[2]); secret_wipe(&P[3]);                      // halves of Y_A = A*alpha and Y_G = G*alpha
 }
 
 // =============================================================================================================
@@ -555,6 +568,7 @@ ACT_FN void issue_thread(const act_ctx* C, size_t i, const u32* req, const u32* 
     const u32* rsrc = rnd + 32 * (rnd_index ? (size_t)rnd_index[i] : i);
     ACT_NOUNROLL for (int k = 0; k < 4; k++) load8(r + 8 * k, rsrc + 8 * k);
     bbs_sign_(C, &X_A, r, ACT_TR_RESPOND, &c, A_enc, &e, &g, &z);
+    secret_wipe(&r);
     store8(out, A_enc); store_scalar(out + 8, e); store_scalar(out + 16, g); store_scalar(out + 24, z); store_scalar(out + 32, c);
     status[i] = ACT_ST_OK;
 }
@@ -806,21 +820,25 @@ ACT_FN void spend_chunk_thread(const act_ctx* C, size_t p, int c, const u32* ite
     }
     store8(cvs + ((size_t)ACT_SPEND_CHUNKS * p + c) * 8, cv);
 }
-// folds the CVs, derives the challenge, sets the final status of the verification
-ACT_FN void spend_finish_thread(const act_ctx* C, size_t p, const u32* proofs, u32* cvs, const u32* flags, u8* status) {
-    (void)C;
-    u32* cv = cvs + (size_t)ACT_SPEND_CHUNKS * p * 8;
-    u32 o[16], m[16];
-    // 16 chunks = perfect binary tree; fold in place level by level
+// Root of the 16-chunk BLAKE3 tree (a perfect binary tree: 8 + 4 + 2 parents, then the root with its XOF block 0) from the
+// chunk CVs an EARLIER kernel wrote.  The CVs are read once through the read-only path and folded in the thread's own
+// storage: nothing is written back to `cvs`, so no load in this kernel ever follows a store to the same address.
+ACT_FN void spend_fold_root(const u32* cvs16, u32* o /* 16 words */) {
+    u32 cv[ACT_SPEND_CHUNKS * 8];
+    ACT_NOUNROLL for (int k = 0; k < ACT_SPEND_CHUNKS; k++) load8(cv + 8 * k, cvs16 + 8 * k);
     ACT_NOUNROLL for (int width = ACT_SPEND_CHUNKS; width > 2; width >>= 1) {
         ACT_NOUNROLL for (int k = 0; k < width / 2; k++) {
-            load8(m, cv + 16 * k); load8(m + 8, cv + 16 * k + 8);
-            b3_compress(B3_IV_, m, 0, 0, 64, B3_PARENT, o);
-            store8(cv + 8 * k, o);
+            b3_compress(B3_IV_, cv + 16 * k, 0, 0, 64, B3_PARENT, o);
+            ACT_UNROLL for (int i = 0; i < 8; i++) cv[8 * k + i] = o[i];
         }
     }
-    load8(m, cv); load8(m + 8, cv + 8);
-    b3_compress(B3_IV_, m, 0, 0, 64, B3_PARENT | B3_ROOT, o);
+    b3_compress(B3_IV_, cv, 0, 0, 64, B3_PARENT | B3_ROOT, o);
+}
+// folds the CVs, derives the challenge, sets the final status of the verification
+ACT_FN void spend_finish_thread(const act_ctx* C, size_t p, const u32* proofs, const u32* cvs, const u32* flags, u8* status) {
+    (void)C;
+    u32 o[16];
+    spend_fold_root(cvs + (size_t)ACT_SPEND_CHUNKS * p * 8, o);
     sc g2 = sc_from_wide(o);
     sc gamma = load_scalar(proofs + (size_t)ACT_PROOF_WORDS * p + 8 * 132);
     u32 fl = flags[p];
@@ -840,7 +858,7 @@ ACT_FN void refund_sign_thread(const act_ctx* C, size_t p, const u32* proofs, co
     u32* out = refunds + 32 * p;
     if (status[p] != ACT_ST_OK) {
         ACT_NOUNROLL for (int k = 0; k < 4; k++) store8_zero(out + 8 * k);
-        store8_zero(nullifiers + 8 * p);
+        if (nullifiers) store8_zero(nullifiers + 8 * p);
         return;
     }
     ge Kp;
@@ -853,9 +871,11 @@ ACT_FN void refund_sign_thread(const act_ctx* C, size_t p, const u32* proofs, co
     u32 A_enc[8];
     sc e, g, z, dummy = sc_zero();
     bbs_sign_(C, &X_A, r, ACT_TR_REFUND, &dummy, A_enc, &e, &g, &z);
+    secret_wipe(&r);
     store8(out, A_enc); store_scalar(out + 8, e); store_scalar(out + 16, g); store_scalar(out + 24, z);
-    // nullifier() = k (:720-722); kwords: the k fields alone (n x 8 words) when the proofs are no longer resident
-    store_scalar(nullifiers + 8 * p, kwords ? load_scalar(kwords + 8 * p) : load_scalar(proofs + (size_t)ACT_PROOF_WORDS * p));
+    // nullifier() = k (:720-722); kwords: the k fields alone (n x 8 words) when the proofs are no longer resident;
+    // nullifiers == nullptr: the verification pass already delivered them (act_batch_spend_verify)
+    if (nullifiers) store_scalar(nullifiers + 8 * p, kwords ? load_scalar(kwords + 8 * p) : load_scalar(proofs + (size_t)ACT_PROOF_WORDS * p));
 }
 
 // =============================================================================================================

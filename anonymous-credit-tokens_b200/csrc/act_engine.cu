@@ -7,10 +7,13 @@
 // There is no CPU path: every entry point needs a CUDA device and fails otherwise.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/random.h>
 
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/act_engine.h"
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(ACT_HEAD_BLOCK, ACT_HEAD_BPS) prove_head_kerne
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < m) prove_head_thread(C, &R, p, p, tokens, items, aux, status);
 }
-__global__ void __launch_bounds__(ACT_HASH_BLOCK) prove_challenge_kernel(size_t m, u32* cvs, u32* gammas) {
+__global__ void __launch_bounds__(ACT_HASH_BLOCK) prove_challenge_kernel(size_t m, const u32* cvs, u32* gammas) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < m) prove_challenge_thread(p, cvs, gammas);
 }
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(ACT_HASH_BLOCK) spend_chunk_kernel(const act_c
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n * ACT_SPEND_CHUNKS) spend_chunk_thread(C, t / ACT_SPEND_CHUNKS, (int)(t % ACT_SPEND_CHUNKS), items, cvs);
 }
-__global__ void __launch_bounds__(ACT_HASH_BLOCK) spend_finish_kernel(const act_ctx* C, size_t n, const u32* proofs, u32* cvs, const u32* flags, u8* status) {
+__global__ void __launch_bounds__(ACT_HASH_BLOCK) spend_finish_kernel(const act_ctx* C, size_t n, const u32* proofs, const u32* cvs, const u32* flags, u8* status) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) spend_finish_thread(C, p, proofs, cvs, flags, status);
 }
@@ -175,6 +178,25 @@ __global__ void __launch_bounds__(ACT_SIGN_BLOCK, ACT_SIGN_BPS) refund_sign_kern
 __global__ void __launch_bounds__(ACT_HEAD_BLOCK, ACT_HEAD_BPS) refund_check_kernel(const act_ctx* C, size_t n, const u32* com, const u32* refund, u8* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) refund_check_thread(C, i, com, refund, status);
+}
+
+// nullifiers of a verification-only pass: item 0 of the transcript is the reduced k (src/lib.rs:720-722); zero for rejected proofs
+__global__ void __launch_bounds__(256) nullifier_kernel(size_t n, const u32* items, const u8* status, u32* nullifiers) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 8) return;
+    size_t p = t >> 3;
+    nullifiers[t] = status[p] == ACT_ST_OK ? items[(size_t)ACT_ITEM_WORDS * p + (t & 7)] : 0u;
+}
+// Overwrites the local memory (stack frames, register spills) the signing kernels left behind: local memory is carved per
+// resident thread slot out of one per-context pool and is NOT cleared between kernels, so a later kernel of the same process
+// could read spilled fragments of alpha or (e+x)^-1.  Every thread slot of the machine (SMs x 2048) writes zeros over a frame
+// larger than any kernel's in this library (ptxas.log: 8.6 KB for issue_kernel).
+#define ACT_SCRUB_WORDS 3072
+__global__ void __launch_bounds__(1024, 2) scrub_local_kernel(u32* sink) {
+    volatile u32 frame[ACT_SCRUB_WORDS];
+#pragma unroll 1
+    for (int i = 0; i < ACT_SCRUB_WORDS; i++) frame[i] = 0u;
+    if (sink && frame[threadIdx.x % ACT_SCRUB_WORDS] != 0u) *sink = 1u;   // keeps the frame alive; never true
 }
 
 // ---- set-up kernels ----
@@ -344,8 +366,13 @@ static int fail_msg(const char* what) { g_err = what; return -1; }
         if (e_ != cudaSuccess) return fail(#call, e_); \
     } while (0)
 
+// Proofs per pipeline chunk (default; act_engine_set_spend_chunk or the environment variable ACT_SPEND_CHUNK change it per
+// engine).  The thread-per-proof stages (head, sign) need about 2 368 warps to fill the machine (148 SMs x 16 warps at 128
+// registers): 65 536 proofs per chunk give 2 048.  Round 1 used 16 384 (3.5 warps per SM in those stages:
+// profiles/r01g_other_kernels.txt); measured on 262 144 proofs (profiles/r02a_chunk_size.txt): 200.6k proofs/s at 16 384,
+// 204.1k at 32 768, 204.8k at 65 536, 205.2k at 131 072.
 #ifndef ACT_SPEND_CHUNK
-#define ACT_SPEND_CHUNK 16384   // proofs per pipeline chunk
+#define ACT_SPEND_CHUNK 65536
 #endif
 #define ACT_SMALL_CHUNK 262144  // requests per chunk for the light-weight paths
 
@@ -356,6 +383,8 @@ struct spend_scratch {
     u32* counter = nullptr;     // work counter of the range kernel (units drawn so far in the current launch)
     unsigned range_grid = 0;
     size_t cap = 0;
+    // recorded after every pipeline that used this scratch set; the next user (possibly on another stream) waits on it
+    cudaEvent_t done = nullptr; bool used = false;
 };
 struct io_slot {  // device staging for the host-buffer entry points
     u8 *in0 = nullptr, *in1 = nullptr, *in2 = nullptr, *out0 = nullptr, *out1 = nullptr, *st = nullptr;
@@ -377,8 +406,15 @@ struct act_engine {
     cudaStream_t copy = nullptr;
     cudaEvent_t io_ready[ACT_IO_SLOTS] = {}, io_done[ACT_IO_SLOTS] = {};
     uint64_t launches = 0;
+    size_t spend_chunk = ACT_SPEND_CHUNK;
+    // multi-device engine (act_engine_create_multi): one single-device engine per GPU; host-buffer calls shard over them
+    std::vector<act_engine*> replicas;
+    // device copy of a call's status + nullifiers (33 B per proof), kept when a screened multi-device call asks for it:
+    // what the NVLink gather to replica 0 reads (act_batch_verify_spend_and_refund_screened)
+    u8 *g_st = nullptr, *g_nul = nullptr; size_t g_cap = 0; bool g_keep = false;
     int32_t* d_skel[4] = {nullptr, nullptr, nullptr, nullptr};   // canonical CBOR skeletons (request, response, proof, refund)
     u32* d_rp_table = nullptr; size_t rp_cap = 0;                 // replay-screen hash table
+    rp_key128 rp_key = {0, 0}; uint64_t rp_calls = 0;             // its PRF key (OS CSPRNG, drawn at creation) and a per-call tweak
     // prover scratch (one chunk): transcript items, half-points, chunk CVs, challenges, r3
     u32 *pv_items = nullptr, *pv_cpts = nullptr, *pv_cvs = nullptr, *pv_gammas = nullptr, *pv_aux = nullptr; size_t pv_cap = 0;
     // optional per-kernel device timing (CUDA events on the launching stream)
@@ -386,6 +422,32 @@ struct act_engine {
     struct timed { int kind; cudaEvent_t a, b; };
     std::vector<timed> events;
 };
+static inline bool is_multi(const act_engine* e) { return !e->replicas.empty(); }
+#define NOT_MULTI(e, what) do { if (is_multi(e)) return fail_msg(what ": device-buffer calls need a single-device engine (act_engine_replica)"); } while (0)
+// call(replica, first index of its shard, shard length) on every replica, each from its own host thread: contiguous shards
+// (bounds of sharding.shard_bounds), no cross-GPU arithmetic
+// first index of shard g of G: sizes differ by at most one, the first n % G shards take the extra request (sharding.shard_bounds)
+static inline size_t shard_lo(size_t n, size_t g, size_t G) { size_t base = n / G, rem = n % G; return g * base + (g < rem ? g : rem); }
+template <typename F>
+static int shard_over(const std::vector<act_engine*>& reps, size_t n, F call) {
+    size_t G = reps.size();
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++) {
+        size_t lo = shard_lo(n, g, G), hi = shard_lo(n, g + 1, G);
+        th.emplace_back([&, g, lo, hi] {
+            rcs[g] = hi > lo ? call(reps[g], lo, hi - lo) : 0;
+            if (rcs[g]) errs[g] = g_err;
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < G; g++) if (rcs[g]) { g_err = "replica " + std::to_string(g) + " (device " + std::to_string(reps[g]->device) + "): " + errs[g]; return rcs[g]; }
+    return 0;
+}
+template <typename F>
+static int shard_over_replicas(act_engine* e, size_t n, F call) { return shard_over(e->replicas, n, call); }
+
 enum { K_RANGE = 0, K_HEAD, K_CHUNK, K_FINISH, K_SIGN, K_ISSUE, K_ISSUANCE_CHECK, K_REFUND_CHECK, K_ENCODE, K_KINDS };
 
 // LAUNCH(e, kind, stream, kernel<<<...>>>(...)) : counts the launch and, when timing is on, brackets it with events
@@ -416,6 +478,7 @@ static int ensure_scratch(spend_scratch* s, size_t n) {
         s->range_grid = (unsigned)(sms * per_sm);
         CK(cudaMalloc((void**)&s->tabs, (size_t)s->range_grid * ACT_RANGE_BLOCK * ACT_RANGE_SPLIT * sizeof(vb_table)));
         CK(cudaMalloc((void**)&s->counter, 4));
+        CK(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
     }
     if (s->cap >= n) return 0;
     cudaFree(s->items); cudaFree(s->com_niels); cudaFree(s->kprime); cudaFree(s->flags); cudaFree(s->cvs); cudaFree(s->cpts);
@@ -477,8 +540,28 @@ static void build_prefix(act_ctx* c, int which, const char* label, const uint8_t
 
 extern "C" void act_engine_destroy(act_engine* e) {
     if (!e) return;
+    if (!e->replicas.empty()) {
+        for (act_engine* r : e->replicas) act_engine_destroy(r);
+        delete e;
+        return;
+    }
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
+    if (e->stream[0]) {   // every staging copy of signer randomness, and the local memory of the signing kernels
+        for (int which = 0; which < 3; which++) {
+            for (int k = 0; k < ACT_IO_SLOTS; k++) {
+                io_slot& io = e->io[k];
+                u8* p = which == 0 ? io.in0 : which == 1 ? io.in1 : io.in2;
+                size_t cap = which == 0 ? io.cap_in0 : which == 1 ? io.cap_in1 : io.cap_in2;
+                if (p && cap) cudaMemsetAsync(p, 0, cap, e->stream[0]);
+            }
+        }
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && sms > 0)
+            scrub_local_kernel<<<sms * 2, 1024, 0, e->stream[0]>>>(nullptr);
+        cudaStreamSynchronize(e->stream[0]);
+    }
+    cudaFree(e->g_st); cudaFree(e->g_nul);
     if (e->d_ctx) { cudaMemset(e->d_ctx, 0, sizeof(act_ctx)); cudaFree(e->d_ctx); }  // zeroise x on the device
     cudaFree(e->d_tables); cudaFree(e->d_bases);
     for (int k = 0; k < 4; k++) cudaFree(e->d_skel[k]);
@@ -489,6 +572,7 @@ extern "C" void act_engine_destroy(act_engine* e) {
     for (int s = 0; s < 2; s++) {
         spend_scratch& sc_ = e->scratch[s];
         cudaFree(sc_.items); cudaFree(sc_.com_niels); cudaFree(sc_.kprime); cudaFree(sc_.flags); cudaFree(sc_.cvs); cudaFree(sc_.tabs); cudaFree(sc_.counter); cudaFree(sc_.cpts);
+        if (sc_.done) cudaEventDestroy(sc_.done);
         if (e->stream[s]) cudaStreamDestroy(e->stream[s]);
     }
     for (int k = 0; k < ACT_IO_SLOTS; k++) {
@@ -528,6 +612,15 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         CKB(cudaEventCreateWithFlags(&e->join[0], cudaEventDisableTiming));
         CKB(cudaEventCreateWithFlags(&e->join[1], cudaEventDisableTiming));
         CKB(cudaMalloc((void**)&e->d_ctx, sizeof(act_ctx)));
+        {   // replay-screen PRF key
+            size_t got = 0;
+            while (got < sizeof e->rp_key) {
+                ssize_t r = getrandom(reinterpret_cast<char*>(&e->rp_key) + got, sizeof e->rp_key - got, 0);
+                if (r <= 0) break;
+                got += (size_t)r;
+            }
+            if (got < sizeof e->rp_key) { rc = fail_msg("act_engine_create: the OS random source (getrandom) failed"); break; }
+        }
         size_t fb_entries = 0;
         fb_layout L = make_fb_layout(&fb_entries);
         CKB(cudaMalloc((void**)&e->d_tables, sizeof(ge_niels) * (fb_entries + ACT_CT_SIZE)));
@@ -546,6 +639,7 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         if (!ok) { rc = fail_msg("act_engine_create: H1/H2/H3/W is not a valid ristretto255 encoding"); break; }
         // context
         act_ctx hc;
+        struct wipe_on_exit { void* p; size_t n; ~wipe_on_exit() { explicit_bzero(p, n); } } hc_guard{&hc, sizeof hc};   // every way out of this block
         memset(&hc, 0, sizeof hc);
         for (int b = 0; b < ACT_FB_BASES; b++) { hc.fb[b].p = e->d_tables + L.offset[b]; hc.fb[b].bits = L.bits[b]; hc.fb[b].win = fb_win_of(L.bits[b]); hc.fb[b].ent = fb_ent_of(L.bits[b]); }
         hc.ct_g = e->d_tables + fb_entries;
@@ -558,7 +652,7 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
         // raw key words; finalize_ctx_kernel reduces them mod l on the device
         memcpy(hc.x.v, sk_x, 32);
         CKB(cudaMemcpy(e->d_ctx, &hc, sizeof hc, cudaMemcpyHostToDevice));
-        memset(&hc, 0, sizeof hc);
+        explicit_bzero(&hc, sizeof hc);
         finalize_ctx_kernel<<<1, 1>>>(e->d_ctx, d_enc + 24, d_ok);
         CKB(cudaGetLastError());
         CKB(cudaDeviceSynchronize());
@@ -569,38 +663,58 @@ extern "C" int act_engine_create(act_engine** out, int device, const uint8_t h[9
     cudaFree(d_enc); cudaFree(d_ok); cudaFree(d_W);
     if (rc) { act_engine_destroy(e); return rc; }
     e->launches += 3;
+    if (const char* env = getenv("ACT_SPEND_CHUNK")) {
+        long v = atol(env);
+        if (v >= 1 && v <= (1l << 22)) e->spend_chunk = (size_t)v;
+    }
     *out = e;
     return 0;
 }
 extern "C" int act_engine_device(const act_engine* e) { return e ? e->device : -1; }
-extern "C" uint64_t act_engine_launch_count(const act_engine* e) { return e ? e->launches : 0; }
+extern "C" int act_engine_set_spend_chunk(act_engine* e, size_t proofs) {
+    if (!e) return fail_msg("null engine");
+    if (proofs < 1 || proofs > ((size_t)1 << 22)) return fail_msg("act_engine_set_spend_chunk: 1 .. 4194304 proofs per chunk");
+    for (act_engine* r : e->replicas) r->spend_chunk = proofs;
+    e->spend_chunk = proofs;
+    return 0;
+}
+extern "C" uint64_t act_engine_launch_count(const act_engine* e) {
+    if (!e) return 0;
+    uint64_t t = e->launches;
+    for (const act_engine* r : e->replicas) t += r->launches;
+    return t;
+}
 
 extern "C" int act_public_key(int device, const uint8_t sk_x[32], uint8_t pk_w[32]) {
     if (!sk_x || !pk_w) return fail_msg("act_public_key: null argument");
     CK(cudaSetDevice(device));
-    ge* d_b = nullptr; ge_niels* d_t = nullptr; u32 *d_x = nullptr, *d_o = nullptr;
-    CK(cudaMalloc((void**)&d_b, sizeof(ge) * ACT_FB_BASES));
-    CK(cudaMalloc((void**)&d_t, sizeof(ge_niels) * ACT_CT_SIZE));
-    CK(cudaMalloc((void**)&d_x, 32)); CK(cudaMalloc((void**)&d_o, 32));
-    ge hb[4];
-    memset(hb, 0, sizeof hb);
-    CK(cudaMemcpy(d_x, sk_x, 32, cudaMemcpyHostToDevice));
-    u32 *d_enc = nullptr, *d_ok = nullptr; ge* d_W = nullptr;
-    // bases[0] = G via the set-up kernel with dummy (identity) encodings
-    CK(cudaMalloc((void**)&d_enc, 128)); CK(cudaMemset(d_enc, 0, 128));
-    CK(cudaMalloc((void**)&d_ok, 4)); CK(cudaMalloc((void**)&d_W, sizeof(ge)));
-    setup_decode_kernel<<<1, 1>>>(d_enc, d_b, d_W, d_ok);
-    build_ct_table_kernel<<<1, ACT_CT_WIN>>>(d_b, d_t);
-    public_key_kernel<<<1, 1>>>(d_t, d_x, d_o);
-    CK(cudaGetLastError());
-    CK(cudaMemcpy(pk_w, d_o, 32, cudaMemcpyDeviceToHost));
-    cudaMemset(d_x, 0, 32);
+    ge *d_b = nullptr, *d_W = nullptr; ge_niels* d_t = nullptr; u32 *d_x = nullptr, *d_o = nullptr, *d_enc = nullptr, *d_ok = nullptr;
+    int rc = 0;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaMalloc((void**)&d_b, sizeof(ge) * ACT_FB_BASES));
+        CKB(cudaMalloc((void**)&d_t, sizeof(ge_niels) * ACT_CT_SIZE));
+        CKB(cudaMalloc((void**)&d_x, 32)); CKB(cudaMalloc((void**)&d_o, 32));
+        // bases[0] = G via the set-up kernel with dummy (identity) encodings
+        CKB(cudaMalloc((void**)&d_enc, 128)); CKB(cudaMemset(d_enc, 0, 128));
+        CKB(cudaMalloc((void**)&d_ok, 4)); CKB(cudaMalloc((void**)&d_W, sizeof(ge)));
+        CKB(cudaMemcpy(d_x, sk_x, 32, cudaMemcpyHostToDevice));
+        setup_decode_kernel<<<1, 1>>>(d_enc, d_b, d_W, d_ok);
+        build_ct_table_kernel<<<1, ACT_CT_WIN>>>(d_b, d_t);
+        public_key_kernel<<<1, 1>>>(d_t, d_x, d_o);
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpy(pk_w, d_o, 32, cudaMemcpyDeviceToHost));
+#undef CKB
+    } while (0);
+    // one way out: the device copy of the secret is overwritten before it is freed, whatever failed above
+    if (d_x) { cudaDeviceSynchronize(); cudaMemset(d_x, 0, 32); }
     cudaFree(d_b); cudaFree(d_t); cudaFree(d_x); cudaFree(d_o); cudaFree(d_enc); cudaFree(d_ok); cudaFree(d_W);
-    return 0;
+    return rc;
 }
 
 extern "C" int act_engine_set_timing(act_engine* e, int enable) {
     if (!e) return fail_msg("null engine");
+    for (act_engine* r : e->replicas) r->timing = enable != 0;
     e->timing = enable != 0;
     return 0;
 }
@@ -609,6 +723,16 @@ extern "C" int act_engine_set_timing(act_engine* e, int enable) {
 // 8 spend_encode.
 extern "C" int act_engine_get_timing(act_engine* e, double ms[9], uint64_t count[9]) {
     if (!e || !ms || !count) return fail_msg("act_engine_get_timing: null argument");
+    if (is_multi(e)) {   // sums over the replicas
+        for (int k = 0; k < K_KINDS; k++) { ms[k] = 0; count[k] = 0; }
+        for (act_engine* r : e->replicas) {
+            double m1[K_KINDS]; uint64_t c1[K_KINDS];
+            int rc = act_engine_get_timing(r, m1, c1);
+            if (rc) return rc;
+            for (int k = 0; k < K_KINDS; k++) { ms[k] += m1[k]; count[k] += c1[k]; }
+        }
+        return 0;
+    }
     CK(cudaSetDevice(e->device));
     for (int k = 0; k < K_KINDS; k++) { ms[k] = 0; count[k] = 0; }
     for (auto& t : e->events) {
@@ -622,37 +746,32 @@ extern "C" int act_engine_get_timing(act_engine* e, double ms[9], uint64_t count
     return 0;
 }
 
-// Integer-multiply roofline of this GPU: sustained rate of 32x32+64->64 multiply-adds (IMAD.WIDE.U32) with
-// operands that change every iteration (a loop-invariant product would be hoisted and the loop would time 64-bit
-// additions instead), in limb-MACs per second.  Eight independent accumulators per thread, 64 warps per SM.
-#define PEAK_ITER 4096
-__global__ void __launch_bounds__(256) int_mul_peak_kernel(u32* out, u32 a0, u32 b0) {
-    u32 a[8], b = (b0 + blockIdx.x) | 1u;
-    u32 c[16];
+// Integer-multiply roofline of this GPU, MEASURED: sustained rate of 32x32+64->64 multiply-adds (IMAD.WIDE.U32 with a
+// 64-bit addend, the instruction the field arithmetic is made of), in limb-MACs per second.
+// Sixteen chains per thread, (hi:lo)_i <- hi_{i+1} * b + (hi:lo)_i: the multiplicand of every step is the high word a
+// neighbouring chain produced one step earlier, so no product is loop-invariant (a hoisted product would time 64-bit
+// additions) and no other instruction is needed to keep it so (round 1 xor-ed the accumulators into the operands: one ALU
+// instruction per multiply, and it read 5.0 T, below what the range kernel sustains).  The loop body is 16 IMAD.WIDE.U32,
+// two register moves on the ALU pipe and uniform-datapath loop control (tests/test_abi.py checks the SASS); 16 warps per SM
+// sub-partition hide the 4-cycle issue interval many times over.
+#define PEAK_ITER 2048
+#define PEAK_CHAINS 16
+__global__ void __launch_bounds__(256) int_mul_peak_kernel(u32* out, u32 b0) {
+    u32 lo[PEAK_CHAINS], hi[PEAK_CHAINS];
+    const u32 b = (b0 + 2u * blockIdx.x) | 1u;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { c[2 * i] = i; c[2 * i + 1] = 0; a[i] = a0 * (threadIdx.x + 1) + i; }
+    for (int i = 0; i < PEAK_CHAINS; i++) { lo[i] = 0x9e3779b9u * (threadIdx.x + 1u) + (u32)i; hi[i] = (u32)i; }
 #pragma unroll 1
     for (int it = 0; it < PEAK_ITER; it++) {
-        // the mad.lo.cc / madc.hi pair is what the field multiplication uses; ptxas fuses it into one IMAD.WIDE.U32
-        // with a 64-bit addend (a plain mad.wide.u32 with a 64-bit accumulator gets split into a multiply and an add)
-        asm volatile(
-            "mad.lo.cc.u32 %0, %16, %24, %0;\n\tmadc.hi.u32 %1, %16, %24, %1;\n\t"
-            "mad.lo.cc.u32 %2, %17, %24, %2;\n\tmadc.hi.u32 %3, %17, %24, %3;\n\t"
-            "mad.lo.cc.u32 %4, %18, %24, %4;\n\tmadc.hi.u32 %5, %18, %24, %5;\n\t"
-            "mad.lo.cc.u32 %6, %19, %24, %6;\n\tmadc.hi.u32 %7, %19, %24, %7;\n\t"
-            "mad.lo.cc.u32 %8, %20, %24, %8;\n\tmadc.hi.u32 %9, %20, %24, %9;\n\t"
-            "mad.lo.cc.u32 %10, %21, %24, %10;\n\tmadc.hi.u32 %11, %21, %24, %11;\n\t"
-            "mad.lo.cc.u32 %12, %22, %24, %12;\n\tmadc.hi.u32 %13, %22, %24, %13;\n\t"
-            "mad.lo.cc.u32 %14, %23, %24, %14;\n\tmadc.hi.u32 %15, %23, %24, %15;"
-            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(c[8]), "+r"(c[9]),
-              "+r"(c[10]), "+r"(c[11]), "+r"(c[12]), "+r"(c[13]), "+r"(c[14]), "+r"(c[15])
-            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b));
 #pragma unroll
-        for (int i = 0; i < 8; i++) a[i] ^= c[2 * i];   // one ALU-pipe instruction per multiply-add keeps the product loop-variant
+        for (int i = 0; i < PEAK_CHAINS; i++) {
+            // the mad.lo.cc / madc.hi pair is what fe_mul uses; ptxas fuses it into one IMAD.WIDE.U32 with a 64-bit addend
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(hi[(i + 1) % PEAK_CHAINS]), "r"(b));
+        }
     }
     u32 s = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) s ^= c[i];
+    for (int i = 0; i < PEAK_CHAINS; i++) s ^= lo[i] ^ hi[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 extern "C" int act_measure_int_mul_peak(int device, double* limb_macs_per_s) {
@@ -660,23 +779,23 @@ extern "C" int act_measure_int_mul_peak(int device, double* limb_macs_per_s) {
     CK(cudaSetDevice(device));
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, device));
-    int blocks = p.multiProcessorCount * 8;
+    int blocks = p.multiProcessorCount * 8;     // 8 x 256 threads = 64 warps per SM, one wave
     u32* out = nullptr;
     CK(cudaMalloc((void**)&out, (size_t)blocks * 256 * 4));
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     double best = 1e30;
-    for (int r = 0; r < 6; r++) {
+    for (int r = 0; r < 8; r++) {   // the first launches also bring the clocks up
         CK(cudaEventRecord(a));
-        int_mul_peak_kernel<<<blocks, 256>>>(out, 3, 5);
+        int_mul_peak_kernel<<<blocks, 256>>>(out, 3);
         CK(cudaEventRecord(b));
         CK(cudaEventSynchronize(b));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, a, b));
-        if (r > 0 && ms < best) best = ms;
+        if (r > 1 && ms < best) best = ms;
     }
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
-    *limb_macs_per_s = (double)blocks * 256 * PEAK_ITER * 8 / (best * 1e-3);
+    *limb_macs_per_s = (double)blocks * 256 * PEAK_ITER * PEAK_CHAINS / (best * 1e-3);
     return 0;
 }
 
@@ -699,6 +818,7 @@ static inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + b
 // ---- device-buffer entry points ----
 extern "C" int act_batch_issue_dev(act_engine* e, size_t n, const void* req, const void* c, const void* rnd, void* resp, void* status, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_batch_issue_dev");
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
@@ -708,6 +828,7 @@ extern "C" int act_batch_issue_dev(act_engine* e, size_t n, const void* req, con
 }
 extern "C" int act_batch_issuance_check_dev(act_engine* e, size_t n, const void* K, const void* resp, void* status, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_batch_issuance_check_dev");
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
@@ -717,6 +838,7 @@ extern "C" int act_batch_issuance_check_dev(act_engine* e, size_t n, const void*
 }
 extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* com, const void* refund, void* status, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_batch_refund_check_dev");
     if (n == 0) return 0;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
@@ -729,6 +851,7 @@ extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* c
 // to the caller (sequential-RNG contract)
 static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, size_t m, const u32* proofs, const u32* rnd,
                               u32* refunds, u32* nullifiers, u8* status, u32* kprime_out = nullptr) {
+    if (s->used) CK(cudaStreamWaitEvent(st, s->done, 0));   // the previous pipeline on this scratch set (any stream) has drained
     CK(cudaMemsetAsync(s->flags, 0, m * 4, st));
     CK(cudaMemsetAsync(s->counter, 0, 4, st));
     size_t rblocks = (m * ACT_L + ACT_RANGE_BLOCK - 1) / ACT_RANGE_BLOCK;   // blocks that would hold one thread per com_j
@@ -742,20 +865,29 @@ static int spend_chunk_launch(act_engine* e, spend_scratch* s, cudaStream_t st, 
     LAUNCH(e, K_FINISH, st, (spend_finish_kernel<<<nblocks(m, ACT_HASH_BLOCK), ACT_HASH_BLOCK, 0, st>>>(e->d_ctx, m, proofs, s->cvs, s->flags, status)));
     if (!kprime_out)
         LAUNCH(e, K_SIGN, st, (refund_sign_kernel<<<nblocks(m, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, m, proofs, rnd, s->kprime, status, refunds, nullifiers)));
+    else if (nullifiers) {   // verification-only pass that also delivers nullifier() of every accepted proof
+        nullifier_kernel<<<nblocks(m * 8, 256), 256, 0, st>>>(m, s->items, status, nullifiers);
+        e->launches += 1;
+    }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(s->done, st));
+    s->used = true;
     return 0;
 }
 extern "C" int act_batch_verify_spend_and_refund_dev(act_engine* e, size_t n, const void* proofs, const void* rnd, void* refunds,
                                                       void* nullifiers, void* status, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_batch_verify_spend_and_refund_dev");
     if (n == 0) return 0;
+    if (!proofs || !rnd || !refunds || !nullifiers || !status) return fail_msg("act_batch_verify_spend_and_refund_dev: null buffer");
     CK(cudaSetDevice(e->device));
     cudaStream_t user = stream ? (cudaStream_t)stream : e->stream[0];
-    size_t cap = n < ACT_SPEND_CHUNK ? n : ACT_SPEND_CHUNK;
+    const size_t ACT_SPEND_CHUNK_RT = e->spend_chunk;
+    size_t cap = n < ACT_SPEND_CHUNK_RT ? n : ACT_SPEND_CHUNK_RT;
     int rc;
     // chunks alternate over the engine's two streams (each with its own scratch) so that the thread-per-proof
     // kernels of one chunk overlap the range kernel of the next; fork from / join into the caller's stream.
-    bool two = n > ACT_SPEND_CHUNK;
+    bool two = n > ACT_SPEND_CHUNK_RT;
     if ((rc = ensure_scratch(&e->scratch[0], cap))) return rc;
     if (two && (rc = ensure_scratch(&e->scratch[1], cap))) return rc;
     if (two) {
@@ -764,8 +896,8 @@ extern "C" int act_batch_verify_spend_and_refund_dev(act_engine* e, size_t n, co
         CK(cudaStreamWaitEvent(e->stream[1], e->fork, 0));
     }
     size_t ci = 0;
-    for (size_t off = 0; off < n; off += ACT_SPEND_CHUNK, ci++) {
-        size_t m = n - off < ACT_SPEND_CHUNK ? n - off : ACT_SPEND_CHUNK;
+    for (size_t off = 0; off < n; off += ACT_SPEND_CHUNK_RT, ci++) {
+        size_t m = n - off < ACT_SPEND_CHUNK_RT ? n - off : ACT_SPEND_CHUNK_RT;
         int slot = two ? (int)(ci & 1) : 0;
         cudaStream_t st = two ? e->stream[slot] : user;
         rc = spend_chunk_launch(e, &e->scratch[slot], st, m, (const u32*)proofs + off * ACT_PROOF_WORDS, (const u32*)rnd + off * 32,
@@ -785,37 +917,85 @@ extern "C" int act_batch_verify_spend_and_refund_dev(act_engine* e, size_t n, co
 struct host_io {
     const uint8_t* in[3]; size_t in_stride[3];
     uint8_t* out[3]; size_t out_stride[3];  // out[2] = status (stride 1)
+    int secret_in = -1;                     // index of the input that carries signer randomness (e_wide | alpha_wide), or -1
 };
+// Leaves no signer randomness behind on the device: zero-fills the staging copies of `rnd` (alpha together with the public
+// (z, gamma, e) yields x) and overwrites the local memory the signing kernels used.  Runs on `st`, asynchronously.
+static int scrub_after_signing(act_engine* e, cudaStream_t st, int secret_in) {
+    for (int k = 0; k < ACT_IO_SLOTS; k++) {
+        io_slot& io = e->io[k];
+        u8* p = secret_in == 0 ? io.in0 : secret_in == 1 ? io.in1 : secret_in == 2 ? io.in2 : nullptr;
+        size_t cap = secret_in == 0 ? io.cap_in0 : secret_in == 1 ? io.cap_in1 : secret_in == 2 ? io.cap_in2 : 0;
+        if (p && cap) CK(cudaMemsetAsync(p, 0, cap, st));
+    }
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    scrub_local_kernel<<<sms * 2, 1024, 0, st>>>(nullptr);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+// Chunk boundaries of a host-buffer call: full chunks, except that a batch of more than one chunk starts with a short ramp
+// (chunk/8, chunk/2) so that the first kernels start after a small H2D copy instead of after a whole chunk's (1.1 GB for
+// 65 536 proofs); the copy stream runs ahead of the compute streams from then on.
+static void chunk_plan(size_t n, size_t chunk, bool ramp, std::vector<size_t>& sizes) {
+    sizes.clear();
+    size_t off = 0;
+    if (ramp && n > chunk && chunk >= 4096) {
+        for (size_t m : {chunk / 8, chunk / 2}) { sizes.push_back(m); off += m; }
+    }
+    while (off < n) { size_t m = n - off < chunk ? n - off : chunk; sizes.push_back(m); off += m; }
+}
 template <typename F>
-static int run_chunked(act_engine* e, size_t n, size_t chunk, const host_io& h, F launch) {
+static int run_chunked(act_engine* e, size_t n, size_t chunk, const host_io& h, F launch, bool ramp = false) {
     CK(cudaSetDevice(e->device));
-    size_t nchunks = (n + chunk - 1) / chunk;
+    std::vector<size_t> sizes;
+    chunk_plan(n, chunk, ramp, sizes);
+    size_t nchunks = sizes.size(), maxm = 0;
+    for (size_t m : sizes) maxm = m > maxm ? m : maxm;
+    // staging of every slot this call will use, sized for its largest chunk BEFORE anything is in flight (growing a slot later
+    // would free memory a running kernel still reads)
+    for (size_t k = 0; k < (nchunks < ACT_IO_SLOTS ? nchunks : (size_t)ACT_IO_SLOTS); k++) {
+        io_slot& io = e->io[k];
+        int rc;
+        if ((rc = ensure(&io.in0, &io.cap_in0, maxm * h.in_stride[0] + 16))) return rc;
+        if (h.in[1] && (rc = ensure(&io.in1, &io.cap_in1, maxm * h.in_stride[1] + 16))) return rc;
+        if (h.in[2] && (rc = ensure(&io.in2, &io.cap_in2, maxm * h.in_stride[2] + 16))) return rc;
+        if (h.out[0] && (rc = ensure(&io.out0, &io.cap_out0, maxm * h.out_stride[0] + 16))) return rc;
+        if (h.out[1] && (rc = ensure(&io.out1, &io.cap_out1, maxm * h.out_stride[1] + 16))) return rc;
+        if ((rc = ensure(&io.st, &io.cap_st, maxm + 16))) return rc;
+    }
+    size_t off = 0;
     for (size_t ci = 0; ci < nchunks; ci++) {
         int s = (int)(ci & 1), k = (int)(ci % ACT_IO_SLOTS);
         io_slot& io = e->io[k];
         cudaStream_t st = e->stream[s];
-        size_t off = ci * chunk, m = n - off < chunk ? n - off : chunk;
+        size_t m = sizes[ci];
         if (ci >= ACT_IO_SLOTS) CK(cudaEventSynchronize(e->io_done[k]));  // slot reuse: chunk ci-3 fully drained (incl. D2H)
         int rc;
-        if ((rc = ensure(&io.in0, &io.cap_in0, m * h.in_stride[0] + 16))) return rc;
-        if (h.in[1] && (rc = ensure(&io.in1, &io.cap_in1, m * h.in_stride[1] + 16))) return rc;
-        if (h.in[2] && (rc = ensure(&io.in2, &io.cap_in2, m * h.in_stride[2] + 16))) return rc;
-        if (h.out[0] && (rc = ensure(&io.out0, &io.cap_out0, m * h.out_stride[0] + 16))) return rc;
-        if (h.out[1] && (rc = ensure(&io.out1, &io.cap_out1, m * h.out_stride[1] + 16))) return rc;
-        if ((rc = ensure(&io.st, &io.cap_st, m + 16))) return rc;
         CK(cudaMemcpyAsync(io.in0, h.in[0] + off * h.in_stride[0], m * h.in_stride[0], cudaMemcpyHostToDevice, e->copy));
         if (h.in[1]) CK(cudaMemcpyAsync(io.in1, h.in[1] + off * h.in_stride[1], m * h.in_stride[1], cudaMemcpyHostToDevice, e->copy));
         if (h.in[2]) CK(cudaMemcpyAsync(io.in2, h.in[2] + off * h.in_stride[2], m * h.in_stride[2], cudaMemcpyHostToDevice, e->copy));
         CK(cudaEventRecord(e->io_ready[k], e->copy));
         CK(cudaStreamWaitEvent(st, e->io_ready[k], 0));
         if ((rc = launch(s, st, m, io))) return rc;
+        if (e->g_keep) {   // screened call: status + nullifiers of the whole shard stay on the device for the gather
+            CK(cudaMemcpyAsync(e->g_st + off, io.st, m, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(e->g_nul + off * 32, io.out1, m * 32, cudaMemcpyDeviceToDevice, st));
+        }
         if (h.out[0]) CK(cudaMemcpyAsync(h.out[0] + off * h.out_stride[0], io.out0, m * h.out_stride[0], cudaMemcpyDeviceToHost, st));
         if (h.out[1]) CK(cudaMemcpyAsync(h.out[1] + off * h.out_stride[1], io.out1, m * h.out_stride[1], cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h.out[2] + off, io.st, m, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(e->io_done[k], st));
+        off += m;
     }
     CK(cudaStreamSynchronize(e->stream[0]));
     CK(cudaStreamSynchronize(e->stream[1]));
+    if (h.secret_in >= 0) {
+        int rc = scrub_after_signing(e, e->stream[0], h.secret_in);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(e->stream[0]));
+    }
     return 0;
 }
 
@@ -823,7 +1003,9 @@ extern "C" int act_batch_issue(act_engine* e, size_t n, const uint8_t* req, cons
     if (!e) return fail_msg("null engine");
     if (n == 0) return 0;
     if (!req || !c || !rnd || !resp || !status) return fail_msg("act_batch_issue: null buffer");
-    host_io h = {{req, c, rnd}, {128, 32, 128}, {resp, nullptr, status}, {160, 0, 1}};
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_batch_issue(r, m, req + lo * 128, c + lo * 32, rnd + lo * 128, resp + lo * 160, status + lo); });
+    host_io h = {{req, c, rnd}, {128, 32, 128}, {resp, nullptr, status}, {160, 0, 1}, 2};
     return run_chunked(e, n, ACT_SMALL_CHUNK, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
         return act_batch_issue_dev(e, m, io.in0, io.in1, io.in2, io.out0, io.st, st);
     });
@@ -832,6 +1014,8 @@ extern "C" int act_batch_issuance_check(act_engine* e, size_t n, const uint8_t* 
     if (!e) return fail_msg("null engine");
     if (n == 0) return 0;
     if (!K || !resp || !status) return fail_msg("act_batch_issuance_check: null buffer");
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_batch_issuance_check(r, m, K + lo * 32, resp + lo * 160, status + lo); });
     host_io h = {{K, resp, nullptr}, {32, 160, 0}, {nullptr, nullptr, status}, {0, 0, 1}};
     return run_chunked(e, n, ACT_SMALL_CHUNK, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
         return act_batch_issuance_check_dev(e, m, io.in0, io.in1, io.st, st);
@@ -841,8 +1025,10 @@ extern "C" int act_batch_refund_check(act_engine* e, size_t n, const uint8_t* co
     if (!e) return fail_msg("null engine");
     if (n == 0) return 0;
     if (!com || !refund || !status) return fail_msg("act_batch_refund_check: null buffer");
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_batch_refund_check(r, m, com + lo * 4096, refund + lo * 128, status + lo); });
     host_io h = {{com, refund, nullptr}, {4096, 128, 0}, {nullptr, nullptr, status}, {0, 0, 1}};
-    return run_chunked(e, n, ACT_SPEND_CHUNK, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
+    return run_chunked(e, n, e->spend_chunk, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
         return act_batch_refund_check_dev(e, m, io.in0, io.in1, io.st, st);
     });
 }
@@ -851,12 +1037,19 @@ extern "C" int act_batch_verify_spend_and_refund(act_engine* e, size_t n, const 
     if (!e) return fail_msg("null engine");
     if (n == 0) return 0;
     if (!proofs || !rnd || !refunds || !nullifiers || !status) return fail_msg("act_batch_verify_spend_and_refund: null buffer");
-    host_io h = {{proofs, rnd, nullptr}, {ACT_PROOF_BYTES, 128, 0}, {refunds, nullifiers, status}, {128, 32, 1}};
-    return run_chunked(e, n, ACT_SPEND_CHUNK, h, [&](int s, cudaStream_t st, size_t m, io_slot& io) {
-        int rc = ensure_scratch(&e->scratch[s], m < ACT_SPEND_CHUNK ? m : ACT_SPEND_CHUNK);
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_batch_verify_spend_and_refund(r, m, proofs + lo * ACT_PROOF_BYTES, rnd + lo * 128, refunds + lo * 128, nullifiers + lo * 32, status + lo); });
+    host_io h = {{proofs, rnd, nullptr}, {ACT_PROOF_BYTES, 128, 0}, {refunds, nullifiers, status}, {128, 32, 1}, 1};
+    // both scratch sets at the size of the largest chunk before anything is in flight
+    {
+        size_t cap = n < e->spend_chunk ? n : e->spend_chunk;
+        int rc = ensure_scratch(&e->scratch[0], cap);
+        if (!rc && n > e->spend_chunk) rc = ensure_scratch(&e->scratch[1], cap);
         if (rc) return rc;
+    }
+    return run_chunked(e, n, e->spend_chunk, h, [&](int s, cudaStream_t st, size_t m, io_slot& io) {
         return spend_chunk_launch(e, &e->scratch[s], st, m, (const u32*)io.in0, (const u32*)io.in1, (u32*)io.out0, (u32*)io.out1, io.st);
-    });
+    }, true);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -865,6 +1058,7 @@ extern "C" int act_batch_verify_spend_and_refund(act_engine* e, size_t n, const 
 extern "C" int act_flag_replays_dev(act_engine* e, size_t n, const void* status, const void* nullifiers, size_t n_seen, const void* seen,
                                     void* status_out, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_flag_replays_dev");
     if (n == 0) return 0;
     if (!status || !nullifiers || !status_out || (n_seen && !seen)) return fail_msg("act_flag_replays_dev: null buffer");
     if (n + n_seen >= 0x7fffffffu) return fail_msg("act_flag_replays_dev: batch too large");
@@ -879,7 +1073,8 @@ extern "C" int act_flag_replays_dev(act_engine* e, size_t n, const void* status,
         e->rp_cap = slots;
     }
     CK(cudaMemsetAsync(e->d_rp_table, 0xff, slots * 4, st));
-    u32 seed = 0x243f6a88u ^ (u32)(e->launches * 0x9e3779b9u);
+    // secret per-engine key, tweaked per call: slots are unpredictable to whoever chose the nullifiers
+    rp_key128 seed = {e->rp_key.k0 ^ (++e->rp_calls * 0x9e3779b97f4a7c15ull), e->rp_key.k1};
     u32 total = (u32)(n + n_seen);
     replay_insert_kernel<<<nblocks(total, 256), 256, 0, st>>>((u32)n, (u32)n_seen, (const u8*)status, (const uint4*)seen, (const uint4*)nullifiers,
                                                              e->d_rp_table, (u32)(slots - 1), seed);
@@ -894,6 +1089,7 @@ extern "C" int act_flag_replays(act_engine* e, size_t n, const uint8_t* status, 
     if (!e) return fail_msg("null engine");
     if (n == 0) return 0;
     if (!status || !nullifiers || !status_out || (n_seen && !seen)) return fail_msg("act_flag_replays: null buffer");
+    if (is_multi(e)) return act_flag_replays(e->replicas[0], n, status, nullifiers, n_seen, seen, status_out);   // the screen is global: one device
     CK(cudaSetDevice(e->device));
     u8 *d_st = nullptr, *d_nul = nullptr, *d_seen = nullptr, *d_out = nullptr;
     int rc = 0;
@@ -924,6 +1120,7 @@ static int ensure_skeleton(act_engine* e, int kind) {
 }
 extern "C" int act_unpack_cbor_dev(act_engine* e, int kind, size_t n, const void* cbor, void* records, void* status, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_unpack_cbor_dev");
     if (n == 0) return 0;
     if (!cbor || !records || !status) return fail_msg("act_unpack_cbor_dev: null buffer");
     CK(cudaSetDevice(e->device));
@@ -938,6 +1135,7 @@ extern "C" int act_unpack_cbor_dev(act_engine* e, int kind, size_t n, const void
 }
 extern "C" int act_encode_cbor_dev(act_engine* e, int kind, size_t n, const void* records, void* cbor, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_encode_cbor_dev");
     if (n == 0) return 0;
     if (!cbor || !records) return fail_msg("act_encode_cbor_dev: null buffer");
     CK(cudaSetDevice(e->device));
@@ -976,6 +1174,8 @@ extern "C" int act_unpack_cbor(act_engine* e, int kind, size_t n, const uint8_t*
     if (n == 0) return 0;
     if (kind < 0 || kind > 3) return fail_msg("bad record kind");
     if (!cbor || !records || !status) return fail_msg("act_unpack_cbor: null buffer");
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_unpack_cbor(r, kind, m, cbor + lo * act_cbor_len(kind), records + lo * act_rec_len(kind), status + lo); });
     return cbor_host_roundtrip(e, kind, n, cbor, act_cbor_len(kind), records, act_rec_len(kind), status, true);
 }
 extern "C" int act_encode_cbor(act_engine* e, int kind, size_t n, const uint8_t* records, uint8_t* cbor) {
@@ -983,6 +1183,8 @@ extern "C" int act_encode_cbor(act_engine* e, int kind, size_t n, const uint8_t*
     if (n == 0) return 0;
     if (kind < 0 || kind > 3) return fail_msg("bad record kind");
     if (!cbor || !records) return fail_msg("act_encode_cbor: null buffer");
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_encode_cbor(r, kind, m, records + lo * act_rec_len(kind), cbor + lo * act_cbor_len(kind)); });
     return cbor_host_roundtrip(e, kind, n, records, act_rec_len(kind), cbor, act_cbor_len(kind), nullptr, false);
 }
 
@@ -992,6 +1194,7 @@ extern "C" int act_encode_cbor(act_engine* e, int kind, size_t n, const uint8_t*
 #define ACT_PROVE_CHUNK 8192
 extern "C" int act_batch_request_dev(act_engine* e, size_t n, const void* pre, const void* rnd, void* req, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_batch_request_dev");
     if (n == 0) return 0;
     if (!pre || !rnd || !req) return fail_msg("act_batch_request_dev: null buffer");
     CK(cudaSetDevice(e->device));
@@ -1004,6 +1207,7 @@ extern "C" int act_batch_request_dev(act_engine* e, size_t n, const void* pre, c
 extern "C" int act_batch_prove_spend_dev(act_engine* e, size_t n, const void* tokens, const void* charges, const void* rnd, const uint8_t seed[32],
                                          uint64_t first_index, void* proofs, void* prerefunds, void* status, void* stream) {
     if (!e) return fail_msg("null engine");
+    NOT_MULTI(e, "act_batch_prove_spend_dev");
     if (n == 0) return 0;
     if (!tokens || !charges || !proofs || !prerefunds || !status || (!rnd && !seed)) return fail_msg("act_batch_prove_spend_dev: null buffer");
     CK(cudaSetDevice(e->device));
@@ -1050,6 +1254,8 @@ extern "C" int act_batch_request(act_engine* e, size_t n, const uint8_t* pre, co
     if (!e) return fail_msg("null engine");
     if (n == 0) return 0;
     if (!pre || !rnd || !req) return fail_msg("act_batch_request: null buffer");
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_batch_request(r, m, pre + lo * 64, rnd + lo * 128, req + lo * 128); });
     CK(cudaSetDevice(e->device));
     u8 *d_pre = nullptr, *d_rnd = nullptr, *d_req = nullptr;
     int rc = 0;
@@ -1071,6 +1277,9 @@ extern "C" int act_batch_prove_spend(act_engine* e, size_t n, const uint8_t* tok
     if (!e) return fail_msg("null engine");
     if (n == 0) return 0;
     if (!tokens || !charges || !proofs || !prerefunds || !status || (!rnd && !seed)) return fail_msg("act_batch_prove_spend: null buffer");
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_batch_prove_spend(r, m, tokens + lo * 160, charges + lo * 32, rnd ? rnd + lo * (size_t)ACT_PROVE_SCALARS * 64 : nullptr, seed, first_index + lo,
+                                     proofs + lo * ACT_PROOF_BYTES, prerefunds + lo * 96, status + lo); });
     CK(cudaSetDevice(e->device));
     u8 *d_tk = nullptr, *d_ch = nullptr, *d_rnd = nullptr, *d_pf = nullptr, *d_pr = nullptr, *d_st = nullptr;
     int rc = 0;
@@ -1093,57 +1302,186 @@ extern "C" int act_batch_prove_spend(act_engine* e, size_t n, const uint8_t* tok
 }
 
 // ---------------------------------------------------------------------------------------------------
-// sequential-RNG contract: outputs identical to a loop of issue() / refund() calls over ONE shared RNG.
-// The reference draws e and alpha only after a request verifies (src/lib.rs:638-643, 842-846), so request i uses the
-// 128 bytes at offset 128 * (number of accepted requests before i) of the caller's stream.  Pass 1 verifies the whole
-// batch, the host turns the accept bits into stream positions, pass 2 signs.
+// multi-device engine: one replica per GPU, contiguous shards, no cross-GPU arithmetic
 // ---------------------------------------------------------------------------------------------------
-static int seq_positions(const std::vector<u8>& st, std::vector<u32>& idx, size_t stream_len, size_t* consumed) {
-    size_t acc = 0;
-    idx.resize(st.size());
-    for (size_t i = 0; i < st.size(); i++) { idx[i] = (u32)acc; if (st[i] == 0) acc++; }
-    if (consumed) *consumed = acc * 128;
-    if (acc * 128 > stream_len) return fail_msg("sequential-RNG call: the RNG stream is shorter than 128 bytes per accepted request");
+extern "C" int act_engine_create_multi(act_engine** out, const int* devices, int n_devices, const uint8_t h[96], const uint8_t sk_x[32], const uint8_t pk_w[32]) {
+    if (!out || !devices || n_devices < 1 || !h || !sk_x || !pk_w) return fail_msg("act_engine_create_multi: bad argument");
+    *out = nullptr;
+    // (a device listed twice gets two replicas: wasteful, but it lets a one-GPU box exercise the sharded path)
+    act_engine* m = new act_engine();
+    m->device = devices[0];
+    for (int i = 0; i < n_devices; i++) {
+        act_engine* r = nullptr;
+        int rc = act_engine_create(&r, devices[i], h, sk_x, pk_w);
+        if (rc) { act_engine_destroy(m); return rc; }
+        m->replicas.push_back(r);
+        m->spend_chunk = r->spend_chunk;
+    }
+    // direct NVLink copies into replica 0 for the gather of status + nullifiers (33 B per proof)
+    cudaSetDevice(devices[0]);
+    for (int i = 1; i < n_devices; i++) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devices[0], devices[i]) == cudaSuccess && can) {
+            cudaError_t pe = cudaDeviceEnablePeerAccess(devices[i], 0);
+            if (pe != cudaSuccess) cudaGetLastError();   // already enabled, or unsupported: cudaMemcpyPeerAsync stages instead
+        }
+    }
+    *out = m;
     return 0;
 }
+extern "C" int act_engine_replica_count(const act_engine* e) { return e ? (e->replicas.empty() ? 1 : (int)e->replicas.size()) : 0; }
+extern "C" act_engine* act_engine_replica(act_engine* e, int i) {
+    if (!e) return nullptr;
+    if (e->replicas.empty()) return i == 0 ? e : nullptr;
+    return (i >= 0 && (size_t)i < e->replicas.size()) ? e->replicas[(size_t)i] : nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// two-pass forms: verification and signing as separate calls.  A host that owns ONE RNG (the reference's
+// `impl CryptoRngCore`, src/lib.rs:626,785) verifies, counts the accepted requests, draws exactly 128 bytes for each of
+// them in slice order -- what a loop of issue() / refund() calls would have drawn (:638-643, 842-846) -- and signs.
+// ---------------------------------------------------------------------------------------------------
+// accepted-before-i positions in the compact randomness; fails if it is shorter than 128 bytes per accepted request
+static int seq_positions(const uint8_t* st, size_t n, std::vector<u32>& idx, size_t stream_len, size_t* consumed) {
+    size_t acc = 0;
+    idx.resize(n);
+    for (size_t i = 0; i < n; i++) { idx[i] = (u32)acc; if (st[i] == 0) acc++; }
+    if (consumed) *consumed = acc * 128;
+    if (acc * 128 > stream_len) return fail_msg("signing pass: the randomness is shorter than 128 bytes per accepted request");
+    return 0;
+}
+static size_t count_accepted(const uint8_t* st, size_t n) { size_t a = 0; for (size_t i = 0; i < n; i++) a += st[i] == 0; return a; }
+
+extern "C" int act_batch_issue_verify(act_engine* e, size_t n, const uint8_t* req, uint8_t* status) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!req || !status) return fail_msg("act_batch_issue_verify: null buffer");
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) { return act_batch_issue_verify(r, m, req + lo * 128, status + lo); });
+    host_io h = {{req, nullptr, nullptr}, {128, 0, 0}, {nullptr, nullptr, status}, {0, 0, 1}};
+    return run_chunked(e, n, ACT_SMALL_CHUNK, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
+        issue_mode_kernel<<<nblocks(m, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, m, (const u32*)io.in0, nullptr, nullptr, nullptr, io.st, ACT_MODE_VERIFY, nullptr);
+        e->launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    });
+}
+extern "C" int act_batch_issue_sign(act_engine* e, size_t n, const uint8_t* req, const uint8_t* c, const uint8_t* status, const uint8_t* rnd, size_t rnd_len,
+                                    uint8_t* resp) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!req || !c || !status || !resp || (!rnd && rnd_len)) return fail_msg("act_batch_issue_sign: null buffer");
+    if (n >= 0xffffffffu) return fail_msg("act_batch_issue_sign: batch too large");
+    if (is_multi(e)) {
+        if (count_accepted(status, n) * 128 > rnd_len) return fail_msg("signing pass: the randomness is shorter than 128 bytes per accepted request");
+        return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+            size_t before = count_accepted(status, lo), mine = count_accepted(status + lo, m);
+            return act_batch_issue_sign(r, m, req + lo * 128, c + lo * 32, status + lo, rnd + before * 128, mine * 128, resp + lo * 160);
+        });
+    }
+    CK(cudaSetDevice(e->device));
+    std::vector<u32> idx;
+    size_t used = 0;
+    int rc = seq_positions(status, n, idx, rnd_len, &used);
+    if (rc) return rc;
+    cudaStream_t st = e->stream[0];
+    u8 *d_req = nullptr, *d_c = nullptr, *d_rnd = nullptr, *d_resp = nullptr, *d_st = nullptr; u32* d_idx = nullptr;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaMalloc((void**)&d_req, n * 128)); CKB(cudaMalloc((void**)&d_c, n * 32)); CKB(cudaMalloc((void**)&d_resp, n * 160));
+        CKB(cudaMalloc((void**)&d_st, n)); CKB(cudaMalloc((void**)&d_idx, n * 4)); CKB(cudaMalloc((void**)&d_rnd, used ? used : 128));
+        CKB(cudaMemcpyAsync(d_req, req, n * 128, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(d_c, c, n * 32, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(d_st, status, n, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
+        if (used) CKB(cudaMemcpyAsync(d_rnd, rnd, used, cudaMemcpyHostToDevice, st));
+        issue_mode_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)d_req, (const u32*)d_c, (const u32*)d_rnd, (u32*)d_resp, d_st, ACT_MODE_SIGN, d_idx);
+        e->launches += 1;
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpyAsync(resp, d_resp, n * 160, cudaMemcpyDeviceToHost, st));
+        CKB(cudaMemsetAsync(d_rnd, 0, used ? used : 128, st));     // the device copy of the signer randomness
+        if (scrub_after_signing(e, st, -1)) { rc = -2; break; }
+        CKB(cudaStreamSynchronize(st));
+#undef CKB
+    } while (0);
+    cudaFree(d_req); cudaFree(d_c); cudaFree(d_rnd); cudaFree(d_resp); cudaFree(d_st); cudaFree(d_idx);
+    return rc;
+}
+extern "C" int act_batch_spend_verify(act_engine* e, size_t n, const uint8_t* proofs, uint8_t* nullifiers, uint8_t* status, uint8_t* kprime) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!proofs || !nullifiers || !status || !kprime) return fail_msg("act_batch_spend_verify: null buffer");
+    if (is_multi(e)) return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+        return act_batch_spend_verify(r, m, proofs + lo * ACT_PROOF_BYTES, nullifiers + lo * 32, status + lo, kprime + lo * 128); });
+    {
+        CK(cudaSetDevice(e->device));
+        size_t cap = n < e->spend_chunk ? n : e->spend_chunk;
+        int rc = ensure_scratch(&e->scratch[0], cap);
+        if (!rc && n > e->spend_chunk) rc = ensure_scratch(&e->scratch[1], cap);
+        if (rc) return rc;
+    }
+    host_io h = {{proofs, nullptr, nullptr}, {ACT_PROOF_BYTES, 0, 0}, {kprime, nullifiers, status}, {128, 32, 1}};
+    return run_chunked(e, n, e->spend_chunk, h, [&](int s, cudaStream_t st, size_t m, io_slot& io) {
+        return spend_chunk_launch(e, &e->scratch[s], st, m, (const u32*)io.in0, nullptr, nullptr, (u32*)io.out1, io.st, (u32*)io.out0);
+    }, true);
+}
+extern "C" int act_batch_refund_sign(act_engine* e, size_t n, const uint8_t* kprime, const uint8_t* status, const uint8_t* rnd, size_t rnd_len, uint8_t* refunds) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!kprime || !status || !refunds || (!rnd && rnd_len)) return fail_msg("act_batch_refund_sign: null buffer");
+    if (n >= 0xffffffffu) return fail_msg("act_batch_refund_sign: batch too large");
+    if (is_multi(e)) {
+        if (count_accepted(status, n) * 128 > rnd_len) return fail_msg("signing pass: the randomness is shorter than 128 bytes per accepted request");
+        return shard_over_replicas(e, n, [&](act_engine* r, size_t lo, size_t m) {
+            size_t before = count_accepted(status, lo), mine = count_accepted(status + lo, m);
+            return act_batch_refund_sign(r, m, kprime + lo * 128, status + lo, rnd + before * 128, mine * 128, refunds + lo * 128);
+        });
+    }
+    CK(cudaSetDevice(e->device));
+    std::vector<u32> idx;
+    size_t used = 0;
+    int rc = seq_positions(status, n, idx, rnd_len, &used);
+    if (rc) return rc;
+    cudaStream_t st = e->stream[0];
+    u8 *d_kp = nullptr, *d_rnd = nullptr, *d_ref = nullptr, *d_st = nullptr; u32* d_idx = nullptr;
+    do {
+#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
+        CKB(cudaMalloc((void**)&d_kp, n * 128)); CKB(cudaMalloc((void**)&d_ref, n * 128)); CKB(cudaMalloc((void**)&d_st, n));
+        CKB(cudaMalloc((void**)&d_idx, n * 4)); CKB(cudaMalloc((void**)&d_rnd, used ? used : 128));
+        CKB(cudaMemcpyAsync(d_kp, kprime, n * 128, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(d_st, status, n, cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
+        if (used) CKB(cudaMemcpyAsync(d_rnd, rnd, used, cudaMemcpyHostToDevice, st));
+        refund_sign_seq_kernel<<<nblocks(n, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, n, nullptr, (const u32*)d_rnd, (const u32*)d_kp, d_st, (u32*)d_ref, nullptr, d_idx, nullptr);
+        e->launches += 1;
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpyAsync(refunds, d_ref, n * 128, cudaMemcpyDeviceToHost, st));
+        CKB(cudaMemsetAsync(d_rnd, 0, used ? used : 128, st));
+        if (scrub_after_signing(e, st, -1)) { rc = -2; break; }
+        CKB(cudaStreamSynchronize(st));
+#undef CKB
+    } while (0);
+    cudaFree(d_kp); cudaFree(d_rnd); cudaFree(d_ref); cudaFree(d_st); cudaFree(d_idx);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sequential-RNG contract: outputs identical to a loop of issue() / refund() calls over ONE shared RNG whose
+// bytes the caller has already laid out as a stream: request i uses the 128 bytes at offset 128 * (accepted requests before i).
+// = verification pass, host scan of the accept bits, signing pass.
+// ---------------------------------------------------------------------------------------------------
 extern "C" int act_batch_issue_seq(act_engine* e, size_t n, const uint8_t* req, const uint8_t* c, const uint8_t* rnd_stream, size_t rnd_stream_len,
                                    uint8_t* resp, uint8_t* status, size_t* consumed) {
     if (!e) return fail_msg("null engine");
     if (consumed) *consumed = 0;
     if (n == 0) return 0;
     if (!req || !c || !resp || !status || (!rnd_stream && rnd_stream_len)) return fail_msg("act_batch_issue_seq: null buffer");
-    if (n >= 0xffffffffu) return fail_msg("act_batch_issue_seq: batch too large");
-    CK(cudaSetDevice(e->device));
-    cudaStream_t st = e->stream[0];
-    u8 *d_req = nullptr, *d_c = nullptr, *d_rnd = nullptr, *d_resp = nullptr, *d_st = nullptr; u32* d_idx = nullptr;
-    int rc = 0;
-    do {
-#define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
-        CKB(cudaMalloc((void**)&d_req, n * 128)); CKB(cudaMalloc((void**)&d_c, n * 32)); CKB(cudaMalloc((void**)&d_resp, n * 160));
-        CKB(cudaMalloc((void**)&d_st, n)); CKB(cudaMalloc((void**)&d_idx, n * 4));
-        CKB(cudaMemcpyAsync(d_req, req, n * 128, cudaMemcpyHostToDevice, st));
-        CKB(cudaMemcpyAsync(d_c, c, n * 32, cudaMemcpyHostToDevice, st));
-        issue_mode_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)d_req, (const u32*)d_c, nullptr, (u32*)d_resp, d_st, ACT_MODE_VERIFY, nullptr);
-        std::vector<u8> hst(n);
-        CKB(cudaMemcpyAsync(hst.data(), d_st, n, cudaMemcpyDeviceToHost, st));
-        CKB(cudaStreamSynchronize(st));
-        std::vector<u32> idx;
-        size_t used = 0;
-        if ((rc = seq_positions(hst, idx, rnd_stream_len, &used))) break;
-        if (consumed) *consumed = used;
-        CKB(cudaMalloc((void**)&d_rnd, used ? used : 128));
-        if (used) CKB(cudaMemcpyAsync(d_rnd, rnd_stream, used, cudaMemcpyHostToDevice, st));
-        CKB(cudaMemcpyAsync(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
-        issue_mode_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)d_req, (const u32*)d_c, (const u32*)d_rnd, (u32*)d_resp, d_st, ACT_MODE_SIGN, d_idx);
-        e->launches += 2;
-        CKB(cudaGetLastError());
-        CKB(cudaMemcpyAsync(resp, d_resp, n * 160, cudaMemcpyDeviceToHost, st));
-        CKB(cudaMemcpyAsync(status, d_st, n, cudaMemcpyDeviceToHost, st));
-        CKB(cudaStreamSynchronize(st));
-#undef CKB
-    } while (0);
-    cudaFree(d_req); cudaFree(d_c); cudaFree(d_rnd); cudaFree(d_resp); cudaFree(d_st); cudaFree(d_idx);
-    return rc;
+    int rc = act_batch_issue_verify(e, n, req, status);
+    if (rc) return rc;
+    size_t used = count_accepted(status, n) * 128;
+    if (used > rnd_stream_len) return fail_msg("sequential-RNG call: the RNG stream is shorter than 128 bytes per accepted request");
+    if ((rc = act_batch_issue_sign(e, n, req, c, status, rnd_stream, used, resp))) return rc;
+    if (consumed) *consumed = used;
+    return 0;
 }
 extern "C" int act_batch_verify_spend_and_refund_seq(act_engine* e, size_t n, const uint8_t* proofs, const uint8_t* rnd_stream, size_t rnd_stream_len,
                                                       uint8_t* refunds, uint8_t* nullifiers, uint8_t* status, size_t* consumed) {
@@ -1151,51 +1489,76 @@ extern "C" int act_batch_verify_spend_and_refund_seq(act_engine* e, size_t n, co
     if (consumed) *consumed = 0;
     if (n == 0) return 0;
     if (!proofs || !refunds || !nullifiers || !status || (!rnd_stream && rnd_stream_len)) return fail_msg("act_batch_verify_spend_and_refund_seq: null buffer");
-    if (n >= 0xffffffffu) return fail_msg("act_batch_verify_spend_and_refund_seq: batch too large");
-    CK(cudaSetDevice(e->device));
-    u8 *d_st = nullptr, *d_rnd = nullptr, *d_ref = nullptr, *d_nul = nullptr; u32 *d_kp = nullptr, *d_idx = nullptr, *d_k = nullptr;
-    u8* d_pf[2] = {nullptr, nullptr};
+    std::vector<uint8_t> kprime(n * 128);
+    int rc = act_batch_spend_verify(e, n, proofs, nullifiers, status, kprime.data());
+    if (rc) return rc;
+    size_t used = count_accepted(status, n) * 128;
+    if (used > rnd_stream_len) return fail_msg("sequential-RNG call: the RNG stream is shorter than 128 bytes per accepted request");
+    if ((rc = act_batch_refund_sign(e, n, kprime.data(), status, rnd_stream, used, refunds))) return rc;
+    if (consumed) *consumed = used;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the issuer's whole batch step in one call: verify + refund on every replica, gather of status + nullifiers (33 B per
+// proof) to replica 0 over NVLink (cudaMemcpyPeerAsync from each replica's device copy), replay screen there.
+// What examples/act.rs:60-77 does per request -- nullifier check, then refund -- for a slice; a proof whose nullifier
+// occurred earlier in the slice or in `seen` gets status 3 (DoubleSpendError) and NO refund (zero-filled, as the reference
+// never calls refund() for it); its nullifier is kept so that the caller can tell which token was replayed.
+// ---------------------------------------------------------------------------------------------------
+static int ensure_gather(act_engine* r, size_t m) {
+    if (r->g_cap >= m) return 0;
+    CK(cudaSetDevice(r->device));
+    cudaFree(r->g_st); cudaFree(r->g_nul);
+    r->g_st = r->g_nul = nullptr; r->g_cap = 0;
+    CK(cudaMalloc((void**)&r->g_st, m + 16));
+    CK(cudaMalloc((void**)&r->g_nul, m * 32 + 16));
+    r->g_cap = m;
+    return 0;
+}
+extern "C" int act_batch_verify_spend_and_refund_screened(act_engine* e, size_t n, const uint8_t* proofs, const uint8_t* rnd, size_t n_seen, const uint8_t* seen,
+                                                           uint8_t* refunds, uint8_t* nullifiers, uint8_t* status) {
+    if (!e) return fail_msg("null engine");
+    if (n == 0) return 0;
+    if (!proofs || !rnd || !refunds || !nullifiers || !status || (n_seen && !seen)) return fail_msg("act_batch_verify_spend_and_refund_screened: null buffer");
+    std::vector<act_engine*> reps = e->replicas.empty() ? std::vector<act_engine*>{e} : e->replicas;
+    size_t G = reps.size();
     int rc = 0;
+    for (size_t g = 0; g < G && !rc; g++) rc = ensure_gather(reps[g], shard_lo(n, g + 1, G) - shard_lo(n, g, G));
+    if (rc) return rc;
+    for (auto* r : reps) r->g_keep = true;
+    if (G == 1) rc = act_batch_verify_spend_and_refund(reps[0], n, proofs, rnd, refunds, nullifiers, status);
+    else {
+        rc = shard_over(reps, n, [&](act_engine* r, size_t lo, size_t m) {
+            return act_batch_verify_spend_and_refund(r, m, proofs + lo * ACT_PROOF_BYTES, rnd + lo * 128, refunds + lo * 128, nullifiers + lo * 32, status + lo); });
+    }
+    for (auto* r : reps) r->g_keep = false;
+    if (rc) return rc;
+    act_engine* r0 = reps[0];
+    CK(cudaSetDevice(r0->device));
+    cudaStream_t st = r0->stream[0];
+    u8 *d_st = nullptr, *d_nul = nullptr, *d_seen = nullptr, *d_out = nullptr;
     do {
 #define CKB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(#call, e_); break; } }
-        size_t cap = n < ACT_SPEND_CHUNK ? n : ACT_SPEND_CHUNK;
-        if ((rc = ensure_scratch(&e->scratch[0], cap)) || (rc = ensure_scratch(&e->scratch[1], cap))) break;
-        CKB(cudaMalloc((void**)&d_st, n)); CKB(cudaMalloc((void**)&d_kp, n * 128)); CKB(cudaMalloc((void**)&d_idx, n * 4));
-        CKB(cudaMalloc((void**)&d_ref, n * 128)); CKB(cudaMalloc((void**)&d_nul, n * 32)); CKB(cudaMalloc((void**)&d_k, n * 32));
-        CKB(cudaMalloc((void**)&d_pf[0], cap * ACT_PROOF_BYTES)); CKB(cudaMalloc((void**)&d_pf[1], cap * ACT_PROOF_BYTES));
-        // pass 1: verification, chunks alternating over the two streams; K' of every proof is kept
-        size_t ci = 0;
-        for (size_t off = 0; off < n && !rc; off += ACT_SPEND_CHUNK, ci++) {
-            size_t m = n - off < ACT_SPEND_CHUNK ? n - off : ACT_SPEND_CHUNK;
-            int s = (int)(ci & 1);
-            CKB(cudaStreamSynchronize(e->stream[s]));
-            CKB(cudaMemcpyAsync(d_pf[s], proofs + off * ACT_PROOF_BYTES, m * ACT_PROOF_BYTES, cudaMemcpyHostToDevice, e->stream[s]));
-            rc = spend_chunk_launch(e, &e->scratch[s], e->stream[s], m, (const u32*)d_pf[s], nullptr, nullptr, nullptr, d_st + off, d_kp + off * 32);
-            // item 0 of the transcript is the reduced k: keep it for the nullifier output of pass 2
-            CKB(cudaMemcpy2DAsync(d_k + off * 8, 32, e->scratch[s].items, (size_t)ACT_ITEM_WORDS * 4, 32, m, cudaMemcpyDeviceToDevice, e->stream[s]));
+        if (G > 1) {
+            CKB(cudaMalloc((void**)&d_st, n)); CKB(cudaMalloc((void**)&d_nul, n * 32));
+            for (size_t g = 0; g < G && !rc; g++) {
+                size_t lo = shard_lo(n, g, G), m = shard_lo(n, g + 1, G) - lo;
+                if (!m) continue;
+                CKB(cudaMemcpyPeerAsync(d_st + lo, r0->device, reps[g]->g_st, reps[g]->device, m, st));
+                CKB(cudaMemcpyPeerAsync(d_nul + lo * 32, r0->device, reps[g]->g_nul, reps[g]->device, m * 32, st));
+            }
+            if (rc) break;
         }
-        if (rc) break;
-        CKB(cudaStreamSynchronize(e->stream[0])); CKB(cudaStreamSynchronize(e->stream[1]));
-        std::vector<u8> hst(n);
-        CKB(cudaMemcpy(hst.data(), d_st, n, cudaMemcpyDeviceToHost));
-        std::vector<u32> idx;
-        size_t used = 0;
-        if ((rc = seq_positions(hst, idx, rnd_stream_len, &used))) break;
-        if (consumed) *consumed = used;
-        CKB(cudaMalloc((void**)&d_rnd, used ? used : 128));
-        cudaStream_t st = e->stream[0];
-        if (used) CKB(cudaMemcpyAsync(d_rnd, rnd_stream, used, cudaMemcpyHostToDevice, st));
-        CKB(cudaMemcpyAsync(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
-        // pass 2: one launch signs every accepted proof with its position in the stream
-        refund_sign_seq_kernel<<<nblocks(n, ACT_SIGN_BLOCK), ACT_SIGN_BLOCK, 0, st>>>(e->d_ctx, n, nullptr, (const u32*)d_rnd, d_kp, d_st, (u32*)d_ref, (u32*)d_nul, d_idx, d_k);
-        e->launches += 1;
+        CKB(cudaMalloc((void**)&d_out, n));
+        if (n_seen) { CKB(cudaMalloc((void**)&d_seen, n_seen * 32)); CKB(cudaMemcpyAsync(d_seen, seen, n_seen * 32, cudaMemcpyHostToDevice, st)); }
+        if ((rc = act_flag_replays_dev(r0, n, G > 1 ? d_st : r0->g_st, G > 1 ? d_nul : r0->g_nul, n_seen, d_seen, d_out, st))) break;
+        CKB(cudaMemcpyAsync(status, d_out, n, cudaMemcpyDeviceToHost, st));
         CKB(cudaStreamSynchronize(st));
-        CKB(cudaGetLastError());
-        CKB(cudaMemcpy(refunds, d_ref, n * 128, cudaMemcpyDeviceToHost));
-        CKB(cudaMemcpy(nullifiers, d_nul, n * 32, cudaMemcpyDeviceToHost));
-        memcpy(status, hst.data(), n);
 #undef CKB
     } while (0);
-    cudaFree(d_st); cudaFree(d_kp); cudaFree(d_idx); cudaFree(d_k); cudaFree(d_ref); cudaFree(d_nul); cudaFree(d_rnd); cudaFree(d_pf[0]); cudaFree(d_pf[1]);
-    return rc;
+    cudaFree(d_st); cudaFree(d_nul); cudaFree(d_seen); cudaFree(d_out);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++) if (status[i] == 3) memset(refunds + i * 128, 0, 128);
+    return 0;
 }

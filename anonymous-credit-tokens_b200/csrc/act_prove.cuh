@@ -150,18 +150,9 @@ ACT_FN void prove_head_thread(const act_ctx* C, const prove_rng* R, size_t p, si
 }
 
 // ---- stage 3: fold the 16 chunk CVs into the challenge gamma (the transcript of :1061-1070 is the verifier's) --------
-ACT_FN void prove_challenge_thread(size_t p, u32* cvs, u32* gammas) {
-    u32* cv = cvs + (size_t)ACT_SPEND_CHUNKS * p * 8;
-    u32 o[16], m[16];
-    ACT_NOUNROLL for (int width = ACT_SPEND_CHUNKS; width > 2; width >>= 1) {
-        ACT_NOUNROLL for (int k = 0; k < width / 2; k++) {
-            load8_rw(m, cv + 16 * k); load8_rw(m + 8, cv + 16 * k + 8);
-            b3_compress(B3_IV_, m, 0, 0, 64, B3_PARENT, o);
-            store8(cv + 8 * k, o);
-        }
-    }
-    load8_rw(m, cv); load8_rw(m + 8, cv + 8);
-    b3_compress(B3_IV_, m, 0, 0, 64, B3_PARENT | B3_ROOT, o);
+ACT_FN void prove_challenge_thread(size_t p, const u32* cvs, u32* gammas) {
+    u32 o[16];
+    spend_fold_root(cvs + (size_t)ACT_SPEND_CHUNKS * p * 8, o);
     store_scalar(gammas + 8 * p, sc_from_wide(o));
 }
 

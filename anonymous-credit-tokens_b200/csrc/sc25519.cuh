@@ -111,8 +111,9 @@ ACT_NOINLINE void sc_invert_(sc* out, const sc* in) {
 }
 ACT_FN sc sc_invert(const sc& a) { sc r; sc_invert_(&r, &a); return r; }
 
-// s/2 mod l (l is odd): (s + (s odd ? l : 0)) >> 1.  Public scalars only (used to halve verification scalars so that
-// the batched double-and-encode of ge25519.cuh yields the encoding of the original point).
+// s/2 mod l (l is odd): (s + (s odd ? l : 0)) >> 1, branch-free (the parity becomes a mask), so it serves public and secret
+// scalars alike: verification scalars are halved so that the batched double-and-encode of ge25519.cuh yields the encoding of
+// the original point, and the signing tail halves (e+x)^-1 and alpha for the same reason (act_device.cuh bbs_sign_).
 ACT_FN sc sc_half(const sc& s) {
     u32 m = 0u - (s.v[0] & 1u);
     u32 t[9];

@@ -45,48 +45,31 @@ def flag_replays(status, nullifiers, seen=None, engine=None):
     src/lib.rs:741-745, examples/act.rs:65-69, src/tests.rs:28-50).  Among ACCEPTED proofs (status 0) the first
     occurrence of a nullifier in slice order keeps status 0; later ones -- and any nullifier present in `seen`
     (uint8[k*32] of previously spent nullifiers) -- are flagged 3 (DoubleSpendError).  Refund outputs are not
-    touched.  Returns a new status tensor.  With `engine` and CUDA tensors the engine's own kernel runs; the torch
-    formulation below serves CPU tensors (gloo tests) and is the semantic reference."""
+    touched.  Returns a new status tensor.  Runs the engine's CUDA kernels (act_flag_replays_dev) on CUDA tensors; there is
+    no other path in the product (the sort-based torch formulation the tests compare against lives in tests/replay_reference.py)."""
     n = status.numel()
     if n == 0:
         return status.clone()
-    if engine is not None and status.is_cuda:
-        # the CUDA replay screen of the engine (act_flag_replays_dev: hash table of lowest index per key)
-        out = torch.empty_like(status)
-        status, nullifiers = status.contiguous(), nullifiers.contiguous()
-        k = 0 if seen is None else seen.numel() // 32
-        seen = seen.contiguous() if k else None
-        sp = seen.data_ptr() if k else None
-        cur = torch.cuda.current_stream(status.device)
-        if cur.cuda_stream != 0:
-            engine.flag_replays_dev(n, status.data_ptr(), nullifiers.data_ptr(), k, sp, out.data_ptr(), cur.cuda_stream)
-        else:
-            # torch is on the legacy default stream, whose handle (0) means "the engine's own stream" in the C ABI: run
-            # on a side stream ordered after the producers of the inputs and before the consumers of the result
-            side = _SIDE.get(status.device)
-            if side is None:
-                side = _SIDE[status.device] = torch.cuda.Stream(device=status.device)
-            side.wait_stream(cur)
-            engine.flag_replays_dev(n, status.data_ptr(), nullifiers.data_ptr(), k, sp, out.data_ptr(), side.cuda_stream)
-            for t in (status, nullifiers, out) + ((seen,) if k else ()):
-                t.record_stream(side)
-            cur.wait_stream(side)
-        return out
-    keys = nullifiers.view(n, 32).contiguous().view(torch.int64).view(n, 4)
-    ok = status == 0
-    if seen is not None and seen.numel():
-        k = seen.numel() // 32
-        allk = torch.cat([seen.view(k, 32).contiguous().view(torch.int64).view(k, 4), keys])
-        first_pos = torch.cat([torch.full((k,), -1, dtype=torch.int64, device=status.device),
-                               torch.where(ok, torch.arange(n, device=status.device), torch.full((n,), n, device=status.device))])
+    if engine is None or not status.is_cuda:
+        raise RuntimeError("flag_replays needs the CUDA engine and CUDA tensors (no CPU path)")
+    # the CUDA replay screen of the engine (act_flag_replays_dev: hash table of lowest index per key)
+    out = torch.empty_like(status)
+    status, nullifiers = status.contiguous(), nullifiers.contiguous()
+    k = 0 if seen is None else seen.numel() // 32
+    seen = seen.contiguous() if k else None
+    sp = seen.data_ptr() if k else None
+    cur = torch.cuda.current_stream(status.device)
+    if cur.cuda_stream != 0:
+        engine.flag_replays_dev(n, status.data_ptr(), nullifiers.data_ptr(), k, sp, out.data_ptr(), cur.cuda_stream)
     else:
-        allk = keys
-        first_pos = torch.where(ok, torch.arange(n, device=status.device), torch.full((n,), n, device=status.device))
-    _, inv = torch.unique(allk, dim=0, return_inverse=True)
-    groups = int(inv.max().item()) + 1
-    first = torch.full((groups,), n, dtype=torch.int64, device=status.device).scatter_reduce(0, inv, first_pos, reduce="amin")
-    mine = inv[-n:]
-    dup = ok & (first[mine] != torch.arange(n, device=status.device))
-    out = status.clone()
-    out[dup] = 3
+        # torch is on the legacy default stream, whose handle (0) means "the engine's own stream" in the C ABI: run
+        # on a side stream ordered after the producers of the inputs and before the consumers of the result
+        side = _SIDE.get(status.device)
+        if side is None:
+            side = _SIDE[status.device] = torch.cuda.Stream(device=status.device)
+        side.wait_stream(cur)
+        engine.flag_replays_dev(n, status.data_ptr(), nullifiers.data_ptr(), k, sp, out.data_ptr(), side.cuda_stream)
+        for t in (status, nullifiers, out) + ((seen,) if k else ()):
+            t.record_stream(side)
+        cur.wait_stream(side)
     return out

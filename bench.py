@@ -447,8 +447,8 @@ def main():
         d_flag = torch.empty_like(d_st)
         eng.flag_replays_dev(n, d_st.data_ptr(), d_nul.data_ptr(), 0, None, d_flag.data_ptr(), stream)
         torch.cuda.synchronize()
-        sharding = importlib.import_module("anonymous-credit-tokens_b200.sharding")
-        flag_ref = sharding.flag_replays(d_st, d_nul)          # sort-based torch formulation: the semantic reference of the screen
+        import replay_reference                                # tests/: sort-based torch formulation, the semantic reference of the screen
+        flag_ref = replay_reference.flag_replays(d_st, d_nul)
         ok_flags = bool((d_flag == flag_ref).all())
         replays = int((d_flag == 3).sum().item())
         # the oracle re-checks a sample of each class that must ACCEPT although it was touched (classes 5, 6)

@@ -40,7 +40,9 @@
  * CUDA error); act_last_error() describes it.  There is no CPU fallback: without a usable CUDA
  * device every compute entry point fails.
  *
- * Threading: one engine may be used from one host thread at a time.  Engines are independent.
+ * Threading: one engine may be used from one host thread at a time (a `_dev` call on a caller's stream is ordered against the
+ * engine's previous pipeline by an event, so calls from different streams do not race on the engine's scratch).  Engines are
+ * independent.
  * The caller owns every buffer.  Host-buffer entry points copy H2D/D2H internally (pinned buffers
  * from act_host_alloc make those copies asynchronous); `_dev` entry points take device pointers
  * (16-byte aligned) and a CUDA stream (cudaStream_t cast to void*, NULL = the engine's stream) and
@@ -81,9 +83,23 @@ ACT_API int act_params_derive(int device, const char* org, const char* service, 
 /* Engine for one (Params, PrivateKey) pair on one GPU.  h = H1|H2|H3 encodings, sk_x = secret scalar
  * (reduced mod l), pk_w = encoding of W = G*x.  Fails if any point does not decode or if pk_w is not G*sk_x. */
 ACT_API int act_engine_create(act_engine** out, int device, const uint8_t h[96], const uint8_t sk_x[32], const uint8_t pk_w[32]);
-/* Zeroises the device and host copies of the secret and frees everything. */
+/* Multi-device engine: one replica of (tables, x, W) per listed GPU of this box (`devices[], n_devices`).
+ * Every HOST-buffer entry point below accepts it and shards the batch over the replicas -- replica g takes the contiguous
+ * range (sizes differ by at most one request), each replica is driven by its own host thread, there is no cross-GPU arithmetic and the
+ * outputs land in the caller's buffers exactly as a single-device call would leave them.  Device-buffer (`_dev`) entry
+ * points take one replica: act_engine_replica(e, g).  A single-device engine is its own replica 0.  (A device listed twice
+ * gets two replicas: no use in production, but a one-GPU box can exercise the sharded path that way.) */
+ACT_API int act_engine_create_multi(act_engine** out, const int* devices, int n_devices, const uint8_t h[96], const uint8_t sk_x[32],
+                                    const uint8_t pk_w[32]);
+ACT_API int act_engine_replica_count(const act_engine* e);
+ACT_API act_engine* act_engine_replica(act_engine* e, int i);
+/* Zeroises the device and host copies of the secret, every staging copy of signer randomness and the local memory of the
+ * signing kernels, then frees everything (replicas included). */
 ACT_API void act_engine_destroy(act_engine* e);
 ACT_API int act_engine_device(const act_engine* e);
+/* Proofs per chunk of the spend pipeline (default 65536; also read from the environment variable ACT_SPEND_CHUNK at creation).
+ * Batches are processed chunk by chunk over two streams; scratch memory is about 57 KB per proof of one chunk, twice. */
+ACT_API int act_engine_set_spend_chunk(act_engine* e, size_t proofs);
 /* PrivateKey::public: W = G*x for a given secret (convenience for key set-up). */
 ACT_API int act_public_key(int device, const uint8_t sk_x[32], uint8_t pk_w[32]);
 
@@ -174,6 +190,30 @@ ACT_API int act_batch_issue_seq(act_engine* e, size_t n, const uint8_t* req, con
                                 uint8_t* resp, uint8_t* status, size_t* consumed);
 ACT_API int act_batch_verify_spend_and_refund_seq(act_engine* e, size_t n, const uint8_t* proofs, const uint8_t* rnd_stream, size_t rnd_stream_len,
                                                    uint8_t* refunds, uint8_t* nullifiers, uint8_t* status, size_t* consumed);
+
+/* Two-pass forms: what a host that owns ONE RNG needs in order to behave exactly like a loop over the reference's calls (an
+ * `impl CryptoRngCore` taken by value, src/lib.rs:626,785, from which e and alpha are drawn only after a request verifies):
+ * verify, count the accepted requests, draw 128 bytes for each of them in slice order, sign.
+ *   act_batch_issue_verify : status[i] = 0 / 1 / 0x81; nothing else is written
+ *   act_batch_issue_sign   : status is the verify pass's; rnd = 128 bytes per ACCEPTED request, in slice order (rnd_len >= that);
+ *                            resp as act_batch_issue (zero-filled for rejected requests)
+ *   act_batch_spend_verify : status, nullifiers (reduced k; zero when rejected) and kprime[n*128] -- K' = sum 2^j com_j in extended
+ *                            coordinates (public: a function of the proof), the only state the signing pass needs
+ *   act_batch_refund_sign  : refunds as act_batch_verify_spend_and_refund
+ * The `_seq` calls above are these two passes around a count of the accept bits. */
+ACT_API int act_batch_issue_verify(act_engine* e, size_t n, const uint8_t* req, uint8_t* status);
+ACT_API int act_batch_issue_sign(act_engine* e, size_t n, const uint8_t* req, const uint8_t* c, const uint8_t* status, const uint8_t* rnd, size_t rnd_len,
+                                 uint8_t* resp);
+ACT_API int act_batch_spend_verify(act_engine* e, size_t n, const uint8_t* proofs, uint8_t* nullifiers, uint8_t* status, uint8_t* kprime /* n*128 */);
+ACT_API int act_batch_refund_sign(act_engine* e, size_t n, const uint8_t* kprime, const uint8_t* status, const uint8_t* rnd, size_t rnd_len,
+                                  uint8_t* refunds);
+
+/* The issuer's whole batch step in one call (what examples/act.rs:60-77 does per request: nullifier check, then refund): verify +
+ * refund on every replica, gather of status + nullifiers (33 B per proof) to replica 0 over NVLink (cudaMemcpyPeerAsync), replay
+ * screen there against the batch itself and `seen`.  A replayed proof gets status 3 (DoubleSpendError) and no refund (zero-filled);
+ * its nullifier is kept.  Single-device engines take the same call (no gather). */
+ACT_API int act_batch_verify_spend_and_refund_screened(act_engine* e, size_t n, const uint8_t* proofs, const uint8_t* rnd, size_t n_seen,
+                                                       const uint8_t* seen, uint8_t* refunds, uint8_t* nullifiers, uint8_t* status);
 
 /* Client-side batch generators, bit-exact with the reference's prover for the same RNG bytes but NOT
  * constant time: they exist to synthesise full-size batches of valid, unique fixtures on the device.

@@ -218,6 +218,122 @@ def mutate_proofs_head(ctx, base):
     return proofs.reshape(-1), rnd.reshape(-1), expect, labels
 
 
+G_ENC = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")   # RFC 9496 generator
+
+
+def _bump(rec, off, t=1):
+    rec[off:off + 32] = np.frombuffer(sc_bytes(sc_int(rec[off:off + 32]) + t), np.uint8)
+
+
+def _noncanon(rec, off):
+    v = int.from_bytes(bytes(rec[off:off + 32]), "little") + ELL
+    if v < 2**256:
+        rec[off:off + 32] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
+
+
+def mutate_refunds(com, refunds):
+    """Tampered Refund records for the client-side check PreRefund::to_credit_token (row a4): every component the
+    reference's tests touch -- e + 1 (src/tests.rs:802-816), A + G, gamma + 1, z + 1 (:1176-1226) -> InvalidRefundProof --
+    plus malformed / identity A, non-canonical scalar encodings (must accept) and commitments that are not the proof's.
+    com: n*4096 (the proofs' com[128]), refunds: n*128 VALID refunds.  Returns (com, refunds, expected_status, labels)."""
+    com = np.ascontiguousarray(com).reshape(-1, 4096).copy(); rf = np.ascontiguousarray(refunds).reshape(-1, 128).copy()
+    n = len(rf)
+    expect = np.zeros(n, np.uint8); labels = ["valid"] * n
+    bad = bad_point_encodings()
+    for i in range(n):
+        kind = i % 10
+        if kind == 1:
+            _bump(rf[i], 32); expect[i] = 4; labels[i] = "e+1"
+        elif kind == 2:
+            rf[i, 0:32] = np.frombuffer(O.point_add(bytes(rf[i, 0:32]), G_ENC), np.uint8); expect[i] = 4; labels[i] = "A+G"
+        elif kind == 3:
+            _bump(rf[i], 64); expect[i] = 4; labels[i] = "gamma+1"
+        elif kind == 4:
+            _bump(rf[i], 96); expect[i] = 4; labels[i] = "z+1"
+        elif kind == 5:
+            rf[i, 0:32] = np.frombuffer(bad[(i // 10) % len(bad)], np.uint8); expect[i] = 0x81; labels[i] = "bad A"
+        elif kind == 6:
+            for off in (32, 64, 96):
+                _noncanon(rf[i], off)
+            labels[i] = "non-canonical scalars"
+        elif kind == 7:   # the refund of ANOTHER spend (valid signature on a different K')
+            rf[i] = rf[(i + 1) % n] if n > 1 else rf[i]; expect[i] = 4 if n > 1 else 0; labels[i] = "refund of another spend"
+        elif kind == 8:
+            j = (7 * i) % 127
+            com[i, 32 * j:32 * j + 32], com[i, 32 * j + 32:32 * j + 64] = com[i, 32 * j + 32:32 * j + 64].copy(), com[i, 32 * j:32 * j + 32].copy()
+            expect[i] = 4; labels[i] = "com[j], com[j+1] swapped"
+        elif kind == 9:
+            if (i // 10) % 2:
+                com[i, 32 * 5:32 * 6] = np.frombuffer(bad[(i // 10 + 2) % len(bad)], np.uint8); expect[i] = 0x81; labels[i] = "bad com"
+            else:
+                rf[i, 0:32] = 0; expect[i] = 4; labels[i] = "A identity"
+    return com.reshape(-1), rf.reshape(-1), expect, labels
+
+
+def mutate_responses(base):
+    """Tampered IssuanceResponse records for PreIssuance::to_credit_token (row a3): e + 1 (src/tests.rs:703-714), e = 0
+    (:836-847), every other component the same way, a K that is not the request's, malformed points, non-canonical scalar
+    encodings (must accept).  Returns (K, responses, expected_status, labels)."""
+    K = base["req"].reshape(-1, 128)[:, :32].copy(); rs = base["resp"].reshape(-1, 160).copy()
+    n = len(rs)
+    expect = np.zeros(n, np.uint8); labels = ["valid"] * n
+    bad = bad_point_encodings()
+    for i in range(n):
+        kind = i % 12
+        if kind == 1:
+            _bump(rs[i], 32); expect[i] = 2; labels[i] = "e+1"
+        elif kind == 2:
+            rs[i, 32:64] = 0; expect[i] = 2; labels[i] = "e=0"
+        elif kind == 3:
+            rs[i, 0:32] = np.frombuffer(O.point_add(bytes(rs[i, 0:32]), G_ENC), np.uint8); expect[i] = 2; labels[i] = "A+G"
+        elif kind == 4:
+            _bump(rs[i], 64); expect[i] = 2; labels[i] = "gamma+1"
+        elif kind == 5:
+            _bump(rs[i], 96); expect[i] = 2; labels[i] = "z+1"
+        elif kind == 6:
+            _bump(rs[i], 128); expect[i] = 2; labels[i] = "c+1"
+        elif kind == 7:
+            rs[i, 0:32] = np.frombuffer(bad[(i // 12) % len(bad)], np.uint8); expect[i] = 0x81; labels[i] = "bad A"
+        elif kind == 8:
+            for off in (32, 64, 96, 128):
+                _noncanon(rs[i], off)
+            labels[i] = "non-canonical scalars"
+        elif kind == 9:
+            K[i] = K[(i + 1) % n] if n > 1 else K[i]; expect[i] = 2 if n > 1 else 0; labels[i] = "K of another request"
+        elif kind == 10:
+            K[i] = np.frombuffer(bad[(i // 12 + 5) % len(bad)], np.uint8); expect[i] = 0x81; labels[i] = "bad K"
+        elif kind == 11:
+            rs[i, 0:32] = 0; expect[i] = 2; labels[i] = "A identity"
+    return K.reshape(-1), rs.reshape(-1), expect, labels
+
+
+def tampered_token_proofs(ctx, n, seed=b"token-tamper"):
+    """prop_token_tampering_detection (src/tests.rs:1898-1927): a valid token whose `a` and `e` are overwritten with a random
+    point and scalar still produces a SpendProof, and refund() must answer InvalidClientSpendProof; variants with only one of
+    the two replaced, and with a = identity (A' = identity -> IdentityPointError, src/lib.rs:787-789).
+    Returns dict(proofs, rnd, expect, labels)."""
+    base = gen_valid(ctx, n, seed=seed, threads=min(os.cpu_count() or 1, 8))
+    st = trip_streams(seed, n)
+    tokens = tokens_from(base, st["pre"]).reshape(n, 160).copy()
+    expect = np.zeros(n, np.uint8); labels = ["valid token"] * n
+    for i in range(n):
+        kind = i % 5
+        rp = O.scalarmult_base(O.sc_reduce64(xof(seed + b"/pt/%d" % i, 64)))
+        re = O.sc_reduce64(xof(seed + b"/sc/%d" % i, 64))
+        if kind == 1:
+            tokens[i, 0:32] = np.frombuffer(rp, np.uint8); tokens[i, 32:64] = np.frombuffer(re, np.uint8); expect[i] = 7; labels[i] = "a, e random"
+        elif kind == 2:
+            tokens[i, 0:32] = np.frombuffer(rp, np.uint8); expect[i] = 7; labels[i] = "a random"
+        elif kind == 3:
+            tokens[i, 32:64] = np.frombuffer(re, np.uint8); expect[i] = 7; labels[i] = "e random"
+        elif kind == 4:
+            tokens[i, 0:32] = 0; expect[i] = 6; labels[i] = "a identity"
+    one = (1).to_bytes(32, "little")
+    proofs = b"".join(ctx.prove_spend(tokens[i].tobytes(), one, xof(seed + b"/prove/%d" % i, O.RND_PROVE))[0] for i in range(n))
+    return dict(proofs=np.frombuffer(proofs, np.uint8).copy(), rnd=np.frombuffer(xof(seed + b"/rnd", 128 * n), np.uint8).copy(),
+                expect=expect, labels=labels, tokens=tokens.reshape(-1))
+
+
 def overspend_proofs(ctx, n, seed=b"overspend"):
     """prove_spend run with s > c (src/tests.rs:366-374,1540-1547) -> InvalidClientSpendProof."""
     rs = np.random.RandomState(5)

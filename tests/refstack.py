@@ -372,3 +372,66 @@ def cbor_proof(pf):
 def cbor_refund(rf):
     import cbor2
     return cbor2.dumps({1: rf["A"], 2: sc_bytes(rf["e"]), 3: sc_bytes(rf["gamma"]), 4: sc_bytes(rf["z"])})
+
+
+# ---- record-level front ends: wire bytes in, status + wire bytes out (include/act_engine.h conventions) ----------------
+# Decode semantics of src/cbor.rs:62-91: a point must be a valid ristretto255 encoding (else CborError::InvalidValue ->
+# 0x81, reported before anything else because decoding precedes the protocol call); scalars are reduced mod l, never rejected.
+ST_OK, ST_BAD_REQUEST, ST_BAD_RESPONSE, ST_BAD_REFUND, ST_IDENTITY, ST_BAD_SPEND, ST_DECODE = 0, 1, 2, 4, 6, 7, 0x81
+
+
+def unpack_proof(b):
+    """SpendProof record (16 832 B, include/act_engine.h) -> dict of reduced scalars and point encodings; None if any of the
+    130 points is not a valid encoding."""
+    b = bytes(b)
+    assert len(b) == 526 * 32
+    f = lambda i: b[32 * i:32 * i + 32]
+    pts = [f(2), f(3)] + [f(4 + j) for j in range(L_BITS)]
+    if not all(is_valid(p) for p in pts):
+        return None
+    return dict(k=sc_int(f(0)), s=sc_int(f(1)), Ap=f(2), Bb=f(3), com=[f(4 + j) for j in range(L_BITS)], gamma=sc_int(f(132)),
+                e_bar=sc_int(f(133)), r2_bar=sc_int(f(134)), r3_bar=sc_int(f(135)), c_bar=sc_int(f(136)), r_bar=sc_int(f(137)),
+                w00=sc_int(f(138)), w01=sc_int(f(139)), gamma0=[sc_int(f(140 + j)) for j in range(L_BITS)],
+                z=[(sc_int(f(268 + 2 * j)), sc_int(f(269 + 2 * j))) for j in range(L_BITS)], k_bar=sc_int(f(524)), s_bar=sc_int(f(525)))
+
+
+def refund_record(H, x, W, proof, rnd128):
+    """-> (status, refund 128 B, nullifier 32 B); zero-filled outputs on reject."""
+    pf = unpack_proof(proof)
+    if pf is None:
+        return ST_DECODE, bytes(128), bytes(32)
+    r = refund(H, x, W, pf, Rng(bytes(rnd128)))
+    if r == "identity":
+        return ST_IDENTITY, bytes(128), bytes(32)
+    if r == "invalid":
+        return ST_BAD_SPEND, bytes(128), bytes(32)
+    return ST_OK, pack_refund(r), sc_bytes(pf["k"])
+
+
+def issue_record(H, x, W, req, c32, rnd128):
+    """-> (status, response 160 B)."""
+    req = bytes(req)
+    if not is_valid(req[:32]):
+        return ST_DECODE, bytes(160)
+    rq = dict(K=req[:32], gamma=sc_int(req[32:64]), k_bar=sc_int(req[64:96]), r_bar=sc_int(req[96:128]))
+    r = issue(H, x, W, rq, sc_int(bytes(c32)), Rng(bytes(rnd128)))
+    if r is None:
+        return ST_BAD_REQUEST, bytes(160)
+    return ST_OK, pack_response(r)
+
+
+def issuance_check_record(H, W, K, resp):
+    K, resp = bytes(K), bytes(resp)
+    if not (is_valid(K) and is_valid(resp[:32])):
+        return ST_DECODE
+    rs = dict(A=resp[:32], e=sc_int(resp[32:64]), gamma=sc_int(resp[64:96]), z=sc_int(resp[96:128]), c=sc_int(resp[128:160]))
+    return ST_OK if issuance_check(H, W, K, rs) else ST_BAD_RESPONSE
+
+
+def refund_check_record(H, W, com4096, refund128):
+    com4096, rf = bytes(com4096), bytes(refund128)
+    com = [com4096[32 * j:32 * j + 32] for j in range(L_BITS)]
+    if not (is_valid(rf[:32]) and all(is_valid(p) for p in com)):
+        return ST_DECODE
+    d = dict(A=rf[:32], e=sc_int(rf[32:64]), gamma=sc_int(rf[64:96]), z=sc_int(rf[96:128]))
+    return ST_OK if refund_check(H, W, com, d) else ST_BAD_REFUND

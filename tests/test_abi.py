@@ -23,6 +23,25 @@ def test_library_exports_all_declared_symbols(act):
     assert declared == set(act.EXPORTED_SYMBOLS)
 
 
+def test_peak_microbenchmark_loop_is_pure_wide_multiplies(act):
+    """act_measure_int_mul_peak must time what it claims: the SASS loop body of int_mul_peak_kernel is 16 IMAD.WIDE.U32 and
+    no other instruction of the multiply pipe (round 1's version carried an xor per multiply and read below the kernel it bounds)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z19int_mul_peak_kernelPjj", act.LIB_PATH], capture_output=True, text=True).stdout
+    ins = re.findall(r"/\*([0-9a-f]{4})\*/\s+([^;]+);", sass)
+    back = [(int(a, 16), op) for a, op in ins if op.strip().startswith(("BRA", "@")) and "BRA" in op and "0x" in op]
+    loops = [(int(re.search(r"0x([0-9a-f]+)", op).group(1), 16), a) for a, op in back if int(re.search(r"0x([0-9a-f]+)", op).group(1), 16) < a]
+    assert loops, "no backward branch found"
+    lo, hi = max(loops, key=lambda t: t[1] - t[0])
+    body = [op.split()[0] if not op.strip().startswith("@") else op.split()[1] for a, op in ((int(a, 16), op) for a, op in ins) if lo <= a <= hi]
+    wide = [o for o in body if o.startswith("IMAD.WIDE.U32")]
+    other_mul = [o for o in body if o.startswith(("IMAD", "FFMA", "DFMA", "HFMA")) and not o.startswith("IMAD.WIDE.U32")]
+    assert len(wide) == 16 and not other_mul, body
+
+
 def test_no_cpu_fallback(act):
     if act.device_count() > 0:
         pytest.skip("a CUDA device is present")
@@ -30,6 +49,8 @@ def test_no_cpu_fallback(act):
         act.Engine(act.Params(bytes(96)), act.PrivateKey(bytes(32), bytes(32)))
     with pytest.raises(act.ActError):
         act.Params.new("a", "b", "c", "d")
+    with pytest.raises(act.ActError):
+        act.Engine(act.Params(bytes(96)), act.PrivateKey(bytes(32), bytes(32)), devices=[0, 1])
 
 
 def test_product_does_not_import_oracle():

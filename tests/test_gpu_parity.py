@@ -119,6 +119,46 @@ def test_wrong_issuer_key(act, octx, base):
         assert (st == 7).all()      # src/tests.rs:2019-2024
 
 
+def test_refund_check_every_tamper_class(engine, octx, base):
+    """Row a4 (PreRefund::to_credit_token, src/lib.rs:1217-1253): e + 1 (src/tests.rs:802-816), A + G, gamma + 1, z + 1
+    (:1176-1226), malformed / identity A, a refund for another spend, swapped or malformed commitments, non-canonical scalar
+    encodings (must accept) -- the engine's status equals the oracle's and the class's expected error."""
+    ref, nul, st = engine.batch_verify_spend_and_refund(base["proofs"], base["rnd"])
+    assert (st == 0).all()
+    com = base["proofs"].reshape(-1, corpus.PROOF_BYTES)[:, 128:128 + 4096].copy().reshape(-1)
+    c2, r2, expect, labels = corpus.mutate_refunds(com, ref)
+    got = engine.batch_refund_check(c2, r2)
+    o_st, _ = octx.batch_refund_check(c2, r2, threads=8)
+    assert got.tolist() == o_st.tolist() == expect.tolist(), [(l, int(g), int(o)) for l, g, o in zip(labels, got, o_st) if g != o]
+    assert set(got.tolist()) == {0, 4, 0x81} and len(set(labels)) >= 10
+
+
+def test_issuance_check_every_tamper_class(engine, octx, base):
+    """Row a3 (PreIssuance::to_credit_token, src/lib.rs:528-562): every response component tampered (src/tests.rs:703-714,
+    836-847), a K that is not the request's, malformed points, non-canonical scalars (accept)."""
+    K, rs, expect, labels = corpus.mutate_responses(base)
+    got = engine.batch_issuance_check(K, rs)
+    o_st, _ = octx.batch_issuance_check(K, rs, threads=8)
+    assert got.tolist() == o_st.tolist() == expect.tolist(), [(l, int(g), int(o)) for l, g, o in zip(labels, got, o_st) if g != o]
+    assert set(got.tolist()) == {0, 2, 0x81}
+
+
+def test_tampered_tokens_are_rejected(engine, octx):
+    """prop_token_tampering_detection (src/tests.rs:1898-1927): proofs made from tokens whose a / e were replaced are rejected
+    with InvalidClientSpendProof (a = identity: IdentityPointError); outputs equal the oracle's bit for bit."""
+    t = corpus.tampered_token_proofs(octx, 20)
+    ref, nul, st = engine.batch_verify_spend_and_refund(t["proofs"], t["rnd"])
+    o_ref, o_nul, o_st, _ = octx.batch_refund(t["proofs"], t["rnd"], threads=8)
+    assert st.tolist() == o_st.tolist() == t["expect"].tolist()
+    assert (ref == o_ref).all() and (nul == o_nul).all()
+    # the device prover given the same tampered tokens produces proofs the engine rejects the same way
+    one = np.frombuffer(b"".join((1).to_bytes(32, "little") for _ in range(20)), np.uint8)
+    p2, _, s2 = engine.batch_prove_spend(t["tokens"], one, seed=corpus.xof(b"tamper-gpu", 32))
+    assert (s2 == 0).all()
+    _, _, st2 = engine.batch_verify_spend_and_refund(p2, t["rnd"])
+    assert st2.tolist() == t["expect"].tolist()
+
+
 def test_empty_and_single(engine, octx, base):
     e = np.zeros(0, np.uint8)
     resp, st = engine.batch_issue(e, e, e)
@@ -168,18 +208,23 @@ def test_ragged_sizes_around_the_resident_grid(engine, octx, base):
     proofs, rnd, expect, labels = corpus.mutate_proofs(octx, base)
     u = len(expect)
     o_ref, o_nul, o_st, _ = octx.batch_refund(proofs, rnd, threads=8)
-    for n in (2, 3, 147, 591, 592, 593, 2369, 16385):
-        idx = (np.arange(n) * 5 + n) % u
-        P = proofs.reshape(u, -1)[idx].reshape(-1).copy(); R = rnd.reshape(u, -1)[idx].reshape(-1).copy()
-        ref, nul, st = engine.batch_verify_spend_and_refund(P, R)
-        assert (st == o_st[idx]).all(), n
-        assert (ref.reshape(n, -1) == o_ref.reshape(u, -1)[idx]).all() and (nul.reshape(n, -1) == o_nul.reshape(u, -1)[idx]).all(), n
+    try:
+        for chunk, sizes in ((65536, (2, 3, 147, 591, 592, 593, 2369)), (4096, (4095, 4097, 16385)), (1000, (2999, 3000, 3001))):
+            engine.set_spend_chunk(chunk)      # sizes just below / at / above the pipeline chunk: one, two and three chunks, two streams
+            for n in sizes:
+                idx = (np.arange(n) * 5 + n) % u
+                P = proofs.reshape(u, -1)[idx].reshape(-1).copy(); R = rnd.reshape(u, -1)[idx].reshape(-1).copy()
+                ref, nul, st = engine.batch_verify_spend_and_refund(P, R)
+                assert (st == o_st[idx]).all(), n
+                assert (ref.reshape(n, -1) == o_ref.reshape(u, -1)[idx]).all() and (nul.reshape(n, -1) == o_nul.reshape(u, -1)[idx]).all(), n
+    finally:
+        engine.set_spend_chunk(65536)
 
 
 def test_large_mixed_adversarial_batch(engine, octx, base):
     """BASELINE config #5 shape at a size the GPU finishes in a second: 40 000 proofs, three quarters of them tampered
-    (every mutation class of SURVEY section 4), crossing the 16 384-proof pipeline chunks and both streams with a ragged
-    tail.  Size-independent property: a tiled batch must give the tiled per-proof answers of the oracle, bit for bit;
+    (every mutation class of SURVEY section 4), crossing the pipeline chunks (65 536 proofs by default; this test sets 16 384) and both streams with
+    a ragged tail.  Size-independent property: a tiled batch must give the tiled per-proof answers of the oracle, bit for bit;
     then the batch replay screen (the caller's nullifier check) flags every repeated accepted nullifier."""
     import importlib
     import torch
@@ -189,14 +234,18 @@ def test_large_mixed_adversarial_batch(engine, octx, base):
     n = 40000
     idx = (np.arange(n) * 7 + 3) % u                      # a permuted tiling, so neighbours differ
     P = proofs.reshape(u, -1)[idx].reshape(-1).copy(); R = rnd.reshape(u, -1)[idx].reshape(-1).copy()
-    ref, nul, st = engine.batch_verify_spend_and_refund(P, R)
+    engine.set_spend_chunk(16384)                         # ramp chunks of 2048 and 8192, then 16384 and a ragged 13376
+    try:
+        ref, nul, st = engine.batch_verify_spend_and_refund(P, R)
+    finally:
+        engine.set_spend_chunk(65536)
     assert (st == o_st[idx]).all()
     assert (ref.reshape(n, -1) == o_ref.reshape(u, -1)[idx]).all() and (nul.reshape(n, -1) == o_nul.reshape(u, -1)[idx]).all()
     assert 0.3 < (st != 0).mean() < 0.9 and set(np.unique(st)) >= {0, 6, 7, 0x81}
     # rejected proofs leave zero-filled outputs
     assert not ref.reshape(n, -1)[st != 0].any() and not nul.reshape(n, -1)[st != 0].any()
     sh = importlib.import_module("anonymous-credit-tokens_b200.sharding")
-    flagged = sh.flag_replays(torch.from_numpy(st).cuda(), torch.from_numpy(nul).cuda()).cpu().numpy()
+    flagged = sh.flag_replays(torch.from_numpy(st).cuda(), torch.from_numpy(nul).cuda(), engine=engine).cpu().numpy()
     seen = set(); exp = st.copy()
     for i in range(n):
         if st[i] == 0:
@@ -283,7 +332,8 @@ def test_replay_screen_kernel(engine):
         t_st, t_nul = torch.from_numpy(st).cuda(), torch.from_numpy(nul.reshape(-1)).cuda()
         t_seen = torch.from_numpy(seen.reshape(-1)).cuda() if k else None
         a = sh.flag_replays(t_st, t_nul, t_seen, engine=engine).cpu().numpy()
-        b = sh.flag_replays(t_st, t_nul, t_seen).cpu().numpy()
+        import replay_reference
+        b = replay_reference.flag_replays(t_st, t_nul, t_seen).cpu().numpy()
         assert (a == exp).all() and (b == exp).all()
 
 
@@ -432,6 +482,7 @@ def test_sequential_rng_contract(engine, octx, base):
             assert not resp[160 * i:160 * i + 160].any()
     assert iused == pos
     # a batch that crosses the pipeline chunk (two streams) still lines up with the stream positions
+    engine.set_spend_chunk(8192)
     u = n; N = 20000
     idx = (np.arange(N) * 11 + 5) % u
     P = proofs.reshape(u, -1)[idx].reshape(-1).copy()
@@ -442,6 +493,7 @@ def test_sequential_rng_contract(engine, octx, base):
     packed = big[:used2].reshape(-1, 128)
     full_rnd = np.zeros((N, 128), np.uint8); full_rnd[acc] = packed
     r3, n3, s3 = engine.batch_verify_spend_and_refund(P, full_rnd.reshape(-1))
+    engine.set_spend_chunk(65536)
     assert (r3 == r2).all() and (n3 == n2).all() and (s3 == s2).all()
 
 
@@ -459,3 +511,115 @@ def test_engine_rejects_inconsistent_key_and_bad_params(act, octx):
     xl = (corpus.sc_int(octx.x) + corpus.ELL).to_bytes(32, "little")
     with act.Engine(act.Params(octx.h), act.PrivateKey(xl, octx.w)) as e:
         assert e.launch_count > 0
+
+
+def test_two_pass_forms_equal_the_one_pass_calls(engine, octx, base):
+    """act_batch_issue_verify/_sign and act_batch_spend_verify / act_batch_refund_sign: the verify pass gives the statuses (and
+    nullifiers) of the one-pass call, and signing with 128 bytes per ACCEPTED request in slice order gives the outputs a loop
+    of reference calls over one RNG gives (src/lib.rs:638-643, 842-846) -- checked against the oracle called one by one."""
+    proofs, rnd, expect, labels = corpus.mutate_proofs(octx, base)
+    n = len(expect)
+    nul, st, kp = engine.batch_spend_verify(proofs)
+    ref1, nul1, st1 = engine.batch_verify_spend_and_refund(proofs, rnd)
+    assert (st == st1).all() and (nul == nul1).all()
+    acc = int((st == 0).sum())
+    stream = np.frombuffer(corpus.xof(b"two-pass", 128 * acc), np.uint8)
+    ref = engine.batch_refund_sign(kp, st, stream)
+    pos = 0
+    for i in range(n):
+        if st[i] == 0:
+            o_st, o_ref, o_nul = octx.refund(proofs[i * corpus.PROOF_BYTES:(i + 1) * corpus.PROOF_BYTES].tobytes(), stream[pos:pos + 128].tobytes())
+            pos += 128
+            assert o_st == 0 and ref[128 * i:128 * i + 128].tobytes() == o_ref and nul[32 * i:32 * i + 32].tobytes() == o_nul, (i, labels[i])
+        else:
+            assert not ref[128 * i:128 * i + 128].any() and not nul[32 * i:32 * i + 32].any()
+    with pytest.raises(Exception):
+        engine.batch_refund_sign(kp, st, stream[:-1])            # one byte short
+    req, cs, irnd, iexp, ilab = corpus.mutate_requests(octx, base)
+    ist = engine.batch_issue_verify(req)
+    resp1, ist1 = engine.batch_issue(req, cs, irnd)
+    assert (ist == ist1).all()
+    acc = int((ist == 0).sum())
+    stream = np.frombuffer(corpus.xof(b"two-pass-issue", 128 * acc), np.uint8)
+    resp = engine.batch_issue_sign(req, cs, ist, stream)
+    pos = 0
+    for i in range(len(iexp)):
+        if ist[i] == 0:
+            o_st, o_resp = octx.issue(req[128 * i:128 * i + 128].tobytes(), cs[32 * i:32 * i + 32].tobytes(), stream[pos:pos + 128].tobytes())
+            pos += 128
+            assert o_st == 0 and resp[160 * i:160 * i + 160].tobytes() == o_resp, (i, ilab[i])
+        else:
+            assert not resp[160 * i:160 * i + 160].any()
+
+
+def _multi_devices(act):
+    """Two replicas: on two GPUs when the box has them, else both on GPU 0 (same sharded code path, same-device "peer" copies)."""
+    return [0, 1] if act.device_count() >= 2 else [0, 0]
+
+
+def test_multi_device_engine_matches_single_device(act, engine, octx, base):
+    """act_engine_create_multi (SURVEY 8b `devices[], n_devices`; 8e: contiguous shards, no cross-GPU arithmetic): every
+    host-buffer call on the multi-device engine returns the single-device bytes -- ragged shard sizes included."""
+    params, key = act.Params(octx.h), act.PrivateKey(octx.x, octx.w)
+    proofs, rnd, expect, labels = corpus.mutate_proofs(octx, base)
+    u = len(expect)
+    req, cs, irnd, iexp, _ = corpus.mutate_requests(octx, base)
+    with act.Engine(params, key, devices=_multi_devices(act)) as m:
+        assert m.replica_count == 2
+        for n in (1, 2, 95, u):
+            P, R = proofs[:n * corpus.PROOF_BYTES], rnd[:n * 128]
+            a, b = m.batch_verify_spend_and_refund(P, R), engine.batch_verify_spend_and_refund(P, R)
+            assert all((x == y).all() for x, y in zip(a, b)), n
+        a, b = m.batch_issue(req, cs, irnd), engine.batch_issue(req, cs, irnd)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+        K = base["req"].reshape(-1, 128)[:, :32].copy().reshape(-1)
+        assert (m.batch_issuance_check(K, base["resp"]) == engine.batch_issuance_check(K, base["resp"])).all()
+        com = proofs.reshape(u, -1)[:, 128:128 + 4096].copy().reshape(-1)
+        ref = engine.batch_verify_spend_and_refund(proofs, rnd)[0]
+        assert (m.batch_refund_check(com, ref) == engine.batch_refund_check(com, ref)).all()
+        # the sequential-RNG contract across shards: replica g starts at the stream position the accepted requests of the
+        # shards before it consumed
+        stream = np.frombuffer(corpus.xof(b"multi-seq", 128 * u), np.uint8)
+        a, b = m.batch_verify_spend_and_refund_seq(proofs, stream), engine.batch_verify_spend_and_refund_seq(proofs, stream)
+        assert all((np.asarray(x) == np.asarray(y)).all() for x, y in zip(a, b))
+        a, b = m.batch_issue_seq(req, cs, stream), engine.batch_issue_seq(req, cs, stream)
+        assert all((np.asarray(x) == np.asarray(y)).all() for x, y in zip(a, b))
+        # a bigger tiled batch crossing the chunk size on every replica
+        m.set_spend_chunk(2048)
+        n = 9001
+        idx = (np.arange(n) * 7 + 1) % u
+        P = proofs.reshape(u, -1)[idx].reshape(-1).copy(); R = rnd.reshape(u, -1)[idx].reshape(-1).copy()
+        o_ref, o_nul, o_st, _ = octx.batch_refund(proofs, rnd, threads=8)
+        r2, n2, s2 = m.batch_verify_spend_and_refund(P, R)
+        assert (s2 == o_st[idx]).all() and (r2.reshape(n, -1) == o_ref.reshape(u, -1)[idx]).all() and (n2.reshape(n, -1) == o_nul.reshape(u, -1)[idx]).all()
+        with pytest.raises(act.ActError):      # device-buffer calls take one replica, not the multi-device handle
+            m.batch_issue_dev(1, 0, 0, 0, 0, 0)
+
+
+def test_screened_batch_call(act, engine, octx, base):
+    """act_batch_verify_spend_and_refund_screened = verify + refund + the caller's nullifier check (examples/act.rs:60-77) over a
+    slice: first valid occurrence wins, later ones and members of `seen` get DoubleSpendError and NO refund; on the
+    multi-device engine the status + nullifier gather crosses devices.  Expected result built from the oracle + a python dict."""
+    proofs, rnd, expect, labels = corpus.mutate_proofs(octx, base)
+    u = len(expect)
+    n = 5000
+    idx = (np.arange(n) * 13 + 2) % u                       # heavy repetition: most accepted proofs are replays
+    P = proofs.reshape(u, -1)[idx].reshape(-1).copy(); R = rnd.reshape(u, -1)[idx].reshape(-1).copy()
+    o_ref, o_nul, o_st, _ = octx.batch_refund(proofs, rnd, threads=8)
+    e_ref = o_ref.reshape(u, -1)[idx].copy(); e_nul = o_nul.reshape(u, -1)[idx].copy(); e_st = o_st[idx].copy()
+    seen = o_nul.reshape(u, -1)[[i for i in range(u) if o_st[i] == 0][:3]].copy()     # three tokens spent before this batch
+    db = {bytes(s) for s in seen}
+    for i in range(n):
+        if e_st[i] == 0:
+            k = bytes(e_nul[i])
+            if k in db:
+                e_st[i] = 3; e_ref[i] = 0
+            db.add(k)
+    assert (e_st == 3).sum() > n // 5 and (e_st == 0).sum() > 10
+    params, key = act.Params(octx.h), act.PrivateKey(octx.x, octx.w)
+    with act.Engine(params, key, devices=_multi_devices(act)) as m:
+        m.set_spend_chunk(1024)
+        for eng in (engine, m):
+            ref, nul, st = eng.batch_verify_spend_and_refund_screened(P, R, seen=seen.reshape(-1))
+            assert (st == e_st).all()
+            assert (ref.reshape(n, -1) == e_ref).all() and (nul.reshape(n, -1) == e_nul).all()

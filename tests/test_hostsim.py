@@ -287,12 +287,13 @@ def test_cbor_skeleton_check_is_exact_at_every_byte(act):
         assert (host_st == 0).all() and host_rec.tobytes() == b"".join(r for _, r in accepted)
 
 
-def test_experimental_bucket_form_of_the_range_pair_is_bit_exact(octx):
-    """ACT_RANGE_BUCKETS=1 (experimental, off in the product build): the right-to-left bucket evaluation of the range-proof pair
-    gives the same refunds, nullifiers and statuses as the oracle on the mutation corpus."""
+def test_window_form_of_the_range_pair_is_bit_exact(octx):
+    """ACT_RANGE_BUCKETS=0 (the A/B alternative; the product and the default host build use the right-to-left bucket form):
+    the left-to-right window evaluation of the range-proof pair gives the same refunds, nullifiers and statuses as the oracle
+    on the mutation corpus."""
     import ctypes as C
     HS.lib()     # builds both host libraries
-    L = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(HS.__file__)), "hostsim", "libact_hostsim_buckets.so"))
+    L = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(HS.__file__)), "hostsim", "libact_hostsim_windows.so"))
     vp, sz = C.c_void_p, C.c_size_t
     L.hs_ctx_create.argtypes = [vp, vp, vp]; L.hs_ctx_create.restype = vp
     L.hs_ctx_destroy.argtypes = [vp]

