@@ -32,6 +32,11 @@ extern "C" {
     pub fn act_params_derive(device: c_int, org: *const c_char, service: *const c_char, deployment: *const c_char,
                              version: *const c_char, h: *mut u8) -> c_int;
     pub fn act_engine_create(out: *mut *mut act_engine, device: c_int, h: *const u8, sk_x: *const u8, pk_w: *const u8) -> c_int;
+    pub fn act_engine_create_multi(out: *mut *mut act_engine, devices: *const c_int, n_devices: c_int, h: *const u8, sk_x: *const u8,
+                                   pk_w: *const u8) -> c_int;
+    pub fn act_engine_replica_count(e: *const act_engine) -> c_int;
+    pub fn act_engine_replica(e: *mut act_engine, i: c_int) -> *mut act_engine;
+    pub fn act_engine_set_spend_chunk(e: *mut act_engine, proofs: usize) -> c_int;
     pub fn act_engine_destroy(e: *mut act_engine);
     pub fn act_engine_device(e: *const act_engine) -> c_int;
     pub fn act_public_key(device: c_int, sk_x: *const u8, pk_w: *mut u8) -> c_int;
@@ -48,6 +53,16 @@ extern "C" {
     pub fn act_batch_verify_spend_and_refund_seq(e: *mut act_engine, n: usize, proofs: *const u8, rnd_stream: *const u8,
                                                  rnd_stream_len: usize, refunds: *mut u8, nullifiers: *mut u8, status: *mut u8,
                                                  consumed: *mut usize) -> c_int;
+
+    // two-pass forms: verify, then sign with 128 bytes of randomness per ACCEPTED request in slice order
+    pub fn act_batch_issue_verify(e: *mut act_engine, n: usize, req: *const u8, status: *mut u8) -> c_int;
+    pub fn act_batch_issue_sign(e: *mut act_engine, n: usize, req: *const u8, c: *const u8, status: *const u8, rnd: *const u8, rnd_len: usize,
+                                resp: *mut u8) -> c_int;
+    pub fn act_batch_spend_verify(e: *mut act_engine, n: usize, proofs: *const u8, nullifiers: *mut u8, status: *mut u8, kprime: *mut u8) -> c_int;
+    pub fn act_batch_refund_sign(e: *mut act_engine, n: usize, kprime: *const u8, status: *const u8, rnd: *const u8, rnd_len: usize,
+                                 refunds: *mut u8) -> c_int;
+    pub fn act_batch_verify_spend_and_refund_screened(e: *mut act_engine, n: usize, proofs: *const u8, rnd: *const u8, n_seen: usize,
+                                                      seen: *const u8, refunds: *mut u8, nullifiers: *mut u8, status: *mut u8) -> c_int;
 
     pub fn act_batch_issue_dev(e: *mut act_engine, n: usize, req: *const c_void, c: *const c_void, rnd: *const c_void, resp: *mut c_void,
                                status: *mut c_void, stream: *mut c_void) -> c_int;

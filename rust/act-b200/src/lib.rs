@@ -51,6 +51,26 @@ impl Engine {
         Ok(Engine { raw })
     }
 
+    /// One handle over several GPUs of the box (`act_engine_create_multi`): every call below shards the slice contiguously
+    /// over one replica per device; results are identical to the single-device engine's.
+    pub fn new_multi(domain: [&str; 4], key: &PrivateKey, devices: &[i32]) -> Result<Self, String> {
+        let c: Vec<std::ffi::CString> = domain.iter().map(|s| std::ffi::CString::new(*s).unwrap()).collect();
+        let mut h = [0u8; 96];
+        if unsafe { sys::act_params_derive(devices[0], c[0].as_ptr(), c[1].as_ptr(), c[2].as_ptr(), c[3].as_ptr(), h.as_mut_ptr()) } != 0 {
+            return Err(last_error());
+        }
+        let kc = key.to_cbor().map_err(|e| format!("{e:?}"))?;
+        if kc.len() != 71 || kc[0] != 0xa2 {
+            return Err("unexpected PrivateKey CBOR layout".into());
+        }
+        let (x, w) = (&kc[4..36], &kc[39..71]);
+        let mut raw = std::ptr::null_mut();
+        if unsafe { sys::act_engine_create_multi(&mut raw, devices.as_ptr(), devices.len() as i32, h.as_ptr(), x.as_ptr(), w.as_ptr()) } != 0 {
+            return Err(last_error());
+        }
+        Ok(Engine { raw })
+    }
+
     /// CBOR items -> fixed records: the canonical skeleton on the device, everything else through the host parser.
     fn unpack(&self, kind: i32, items: &[Vec<u8>], cbor_len: usize, rec_len: usize) -> (Vec<u8>, Vec<u8>) {
         let n = items.len();
@@ -85,7 +105,8 @@ impl Engine {
         (rec, st)
     }
 
-    /// Batch form of `PrivateKey::issue` (src/lib.rs:621-663) with the semantics of a loop over ONE shared RNG.
+    /// Batch form of `PrivateKey::issue` (src/lib.rs:621-663) with the semantics of a loop over ONE shared RNG: same outputs, and
+    /// the same RNG state afterwards (128 bytes drawn per accepted request, none for a rejected one).
     pub fn batch_issue(&self, reqs: &[IssuanceRequest], cs: &[Scalar], mut rng: impl CryptoRngCore)
         -> Vec<Result<IssuanceResponse, Error>> {
         let n = reqs.len();
@@ -95,12 +116,18 @@ impl Engine {
         debug_assert!(pst.iter().all(|&s| s == 0));
         let mut c = vec![0u8; 32 * n];
         for (i, s) in cs.iter().enumerate() { c[32 * i..32 * i + 32].copy_from_slice(s.as_bytes()); }
-        let mut stream = vec![0u8; 128 * n];
-        rng.fill_bytes(&mut stream);
-        let (mut resp, mut st, mut used) = (vec![0u8; sys::ACT_RESPONSE_BYTES * n], vec![0u8; n], 0usize);
-        let rc = unsafe { sys::act_batch_issue_seq(self.raw, n, rec.as_ptr(), c.as_ptr(), stream.as_ptr(), stream.len(),
-                                                   resp.as_mut_ptr(), st.as_mut_ptr(), &mut used) };
+        // Verify first, then draw: the reference takes e and alpha from the RNG only after a request verifies
+        // (src/lib.rs:638-643), so a loop of issue() calls leaves the caller's RNG advanced by 128 bytes per ACCEPTED request.
+        // Drawing exactly that many bytes, in slice order, leaves `rng` in the same state as the loop would.
+        let (mut resp, mut st) = (vec![0u8; sys::ACT_RESPONSE_BYTES * n], vec![0u8; n]);
+        let rc = unsafe { sys::act_batch_issue_verify(self.raw, n, rec.as_ptr(), st.as_mut_ptr()) };
         assert_eq!(rc, 0, "{}", last_error());
+        let accepted = st.iter().filter(|&&s| s == 0).count();
+        let mut stream = vec![0u8; 128 * accepted];
+        for chunk in stream.chunks_mut(64) { rng.fill_bytes(chunk); }   // one 64-byte draw per Scalar::random, as the reference does
+        let rc = unsafe { sys::act_batch_issue_sign(self.raw, n, rec.as_ptr(), c.as_ptr(), st.as_ptr(), stream.as_ptr(), stream.len(), resp.as_mut_ptr()) };
+        assert_eq!(rc, 0, "{}", last_error());
+        stream.iter_mut().for_each(|b| *b = 0);
         let mut cb = vec![0u8; sys::ACT_CBOR_RESPONSE_BYTES * n];
         unsafe { sys::act_encode_cbor(self.raw, sys::ACT_KIND_RESPONSE, n, resp.as_ptr(), cb.as_mut_ptr()) };
         (0..n).map(|i| if st[i] == 0 {
@@ -115,12 +142,16 @@ impl Engine {
         let items: Vec<Vec<u8>> = proofs.iter().map(|p| p.to_cbor().expect("to_cbor")).collect();
         let (rec, pst) = self.unpack(sys::ACT_KIND_PROOF, &items, sys::ACT_CBOR_PROOF_BYTES, sys::ACT_PROOF_BYTES);
         debug_assert!(pst.iter().all(|&s| s == 0));
-        let mut stream = vec![0u8; 128 * n];
-        rng.fill_bytes(&mut stream);
-        let (mut refunds, mut nul, mut st, mut used) = (vec![0u8; 128 * n], vec![0u8; 32 * n], vec![0u8; n], 0usize);
-        let rc = unsafe { sys::act_batch_verify_spend_and_refund_seq(self.raw, n, rec.as_ptr(), stream.as_ptr(), stream.len(),
-                                                                     refunds.as_mut_ptr(), nul.as_mut_ptr(), st.as_mut_ptr(), &mut used) };
+        // verify, count, draw 128 bytes per accepted proof in slice order (src/lib.rs:842-846), sign: see batch_issue
+        let (mut refunds, mut nul, mut st, mut kprime) = (vec![0u8; 128 * n], vec![0u8; 32 * n], vec![0u8; n], vec![0u8; 128 * n]);
+        let rc = unsafe { sys::act_batch_spend_verify(self.raw, n, rec.as_ptr(), nul.as_mut_ptr(), st.as_mut_ptr(), kprime.as_mut_ptr()) };
         assert_eq!(rc, 0, "{}", last_error());
+        let accepted = st.iter().filter(|&&s| s == 0).count();
+        let mut stream = vec![0u8; 128 * accepted];
+        for chunk in stream.chunks_mut(64) { rng.fill_bytes(chunk); }
+        let rc = unsafe { sys::act_batch_refund_sign(self.raw, n, kprime.as_ptr(), st.as_ptr(), stream.as_ptr(), stream.len(), refunds.as_mut_ptr()) };
+        assert_eq!(rc, 0, "{}", last_error());
+        stream.iter_mut().for_each(|b| *b = 0);
         let mut cb = vec![0u8; sys::ACT_CBOR_REFUND_BYTES * n];
         unsafe { sys::act_encode_cbor(self.raw, sys::ACT_KIND_REFUND, n, refunds.as_ptr(), cb.as_mut_ptr()) };
         (0..n).map(|i| if st[i] == 0 {
