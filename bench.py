@@ -38,13 +38,16 @@ UNIT = "proofs/s"
 # a wNAF formulation -- the implemented shared-chain / wide-window / batched-encode algorithm needs less):
 #   range kernel per com_j (bucket form, the default since round 2): 1266 S + 2525 M = 2.375e5 -> x128 = 3.04e7 per proof
 #       (round 1's window form: 1506 S + 2583 M = 2.522e5 -> 3.23e7; the constant follows the algorithm that runs)
-#   encode 7.1e5, head 8.2e5 (A1 as a two-term sum, A-bar never formed; the h2 terms of j = 0), sign 3.9e5 (A and Y_A share a doubling chain) per proof
+#       = the EXECUTED IMAD.WIDE lane count ncu reports for the kernel (3.0396e7 per proof, profiles/r02e_spend_range.txt)
+#   the other stages: the executed IMAD.WIDE(.X) lane counts of one ncu capture each at the product launch shape
+#   (profiles/r02f_*.txt): encode 6.81e5, head 7.43e5, sign 3.40e5 per proof, issue 5.37e5 per request.  (Round 1's hand counts --
+#   7.1e5 / 8.2e5 / 3.9e5 / 6.0e5 -- were 4-13 % too high; the constants below are what the kernels execute.)
 LIMB_MACS_PER_SPEND_RANGE = 128 * (1266 * 44 + 2525 * 72)      # 3.040e7
-LIMB_MACS_PER_SPEND_HEAD = 8.2e5
-LIMB_MACS_PER_SPEND_SIGN = 3.9e5
-LIMB_MACS_PER_SPEND_ENCODE = 7.1e5
+LIMB_MACS_PER_SPEND_HEAD = 7.43e5
+LIMB_MACS_PER_SPEND_SIGN = 3.40e5
+LIMB_MACS_PER_SPEND_ENCODE = 6.81e5
 LIMB_MACS_PER_SPEND = LIMB_MACS_PER_SPEND_RANGE + LIMB_MACS_PER_SPEND_ENCODE + LIMB_MACS_PER_SPEND_HEAD + LIMB_MACS_PER_SPEND_SIGN
-LIMB_MACS_PER_ISSUE = 6.0e5
+LIMB_MACS_PER_ISSUE = 5.37e5
 MIXED_N_1GPU = 1 << 22               # BASELINE configs[4]: 4M requests on one GPU
 STRONG_TOTAL = 1 << 23               # BASELINE configs[3]: the SAME 8M-proof batch split over 2/4/8 GPUs
 # IMAD.WIDE.U32 issues at 32 lanes per clock per SM on sm_100 (ncu: 2 fma-heavy pipe cycles per warp instruction at
@@ -744,7 +747,7 @@ def main():
                       "kernel_ms": issue_kernel_ms,
                       "roofline_frac": LIMB_MACS_PER_ISSUE * ni / (issue_kernel_ms * 1e-3) / peak if issue_kernel_ms else None,
                       "roofline_frac_of_model": LIMB_MACS_PER_ISSUE * ni / (issue_kernel_ms * 1e-3) / peak_model if issue_kernel_ms else None,
-                      "work_per_unit": f"{LIMB_MACS_PER_ISSUE:.3g} limb-MACs per request (DESIGN.md 4; executed IMAD.WIDE count per request in profiles/r02*_issue_kernel.txt)"},
+                      "work_per_unit": f"{LIMB_MACS_PER_ISSUE:.3g} limb-MACs per request = the executed IMAD.WIDE(.X) lane count of issue_kernel (ncu, profiles/r02f_issue_kernel.txt)"},
             "mixed_adversarial": mixed,
             "strong_scaling": strong,
             "multi_abi": multi_abi,
