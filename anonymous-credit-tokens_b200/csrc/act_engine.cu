@@ -1042,6 +1042,7 @@ extern "C" int act_batch_verify_spend_and_refund(act_engine* e, size_t n, const 
     host_io h = {{proofs, rnd, nullptr}, {ACT_PROOF_BYTES, 128, 0}, {refunds, nullifiers, status}, {128, 32, 1}, 1};
     // both scratch sets at the size of the largest chunk before anything is in flight
     {
+        CK(cudaSetDevice(e->device));
         size_t cap = n < e->spend_chunk ? n : e->spend_chunk;
         int rc = ensure_scratch(&e->scratch[0], cap);
         if (!rc && n > e->spend_chunk) rc = ensure_scratch(&e->scratch[1], cap);
