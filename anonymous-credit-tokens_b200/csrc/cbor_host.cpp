@@ -6,8 +6,12 @@
 // keys ignored (:134, :381), duplicate keys: last wins, missing field -> InvalidStructure
 // (:138-143, :385-403).  Point *validity* is left to the device (status 0x81).
 //
-// Known divergence: an item carrying BOTH an undecodable point and a later structural defect is
-// reported as 0x82 here, while the reference returns whichever error comes first in map order.
+// Known divergences (both only on malformed or non-canonical items):
+//  * an item carrying BOTH an undecodable point and a later structural defect is reported as 0x82 here, while the
+//    reference returns whichever error comes first in map order;
+//  * duplicate keys: the last value wins here as there, but the reference decodes EVERY occurrence (`decode_point(&val)?`
+//    inside the loop over the map), so an item whose earlier, overwritten occurrence of a point key holds an undecodable
+//    point is an InvalidValue there and is accepted here (only the surviving value reaches the device's validity check).
 #include <stdint.h>
 #include <string.h>
 

@@ -47,6 +47,19 @@ def test_rfc9496_invalid_encodings_rejected():
             assert not R.is_valid(b)
 
 
+def test_rfc9496_hash_to_group_vectors():
+    """RFC 9496 Appendix A.3 (one-way map applied to SHA-512 of the label): three of its vectors.  This is the map behind
+    RistrettoPoint::from_uniform_bytes, i.e. behind Params::new (src/lib.rs:320-353)."""
+    vectors = [("Ristretto is traditionally a short shot of espresso coffee", "3066f82a1a747d45120d1740f14358531a8f04bbffe6a819f86dfe50f44a0a46"),
+               ("This produces a concentrated shot of coffee per volume.", "ae81e7dedf20a497e10c304a765c1767a42d6e06029758d2d7e8ef7cc4c41179"),
+               ("Just pulling a normal shot short will produce a weaker shot", "e2705652ff9f5e44d3e841bf1c251cf7dddb77d140870d1ab2ed64f1a9ce8628")]
+    for label, hx in vectors:
+        u = hashlib.sha512(label.encode()).digest()
+        assert O.from_uniform(u).hex() == hx
+        if R.available():
+            assert R.from_hash(u).hex() == hx
+
+
 def test_field_and_scalar_arithmetic_vs_python_ints():
     rnd = random.Random(3)
     for it in range(200):
