@@ -389,8 +389,11 @@ ACT_NOINLINE void vb_mul_ct_(ge* out, const ge* P, const sc* s) {
 // s1 * P and s2 * P for two SECRET scalars on one base (the signing tail: A = X_A * (e+x)^-1 and Y_A = A * alpha =
 // X_A * (alpha (e+x)^-1)): the doubling chain of the base is shared as in the range kernel -- 192 + 2 x 60 doublings instead
 // of 2 x 252 -- and every lookup scans its whole table (no secret-dependent address or branch).
+#ifndef ACT_SIGN_SPLIT
+#define ACT_SIGN_SPLIT 4
+#endif
 ACT_NOINLINE void vb_mul2_ct_(ge* out1, ge* out2, const ge* P, const sc* s1, const sc* s2) {
-    const int M = 4, WIN = 64 / M;
+    const int M = ACT_SIGN_SPLIT, WIN = 64 / M;
     vb_table t[M];
     vb_split_tables<M>(*P, t);
     ACT_NOUNROLL for (int w = 0; w < 2; w++) {
@@ -677,11 +680,15 @@ ACT_FN void spend_range_thread(const act_ctx* C, size_t p, int j, const u32* pro
 }
 
 // =============================================================================================================
-// spend verification, stage 1b: encode the 256 half-commitments of a proof.  One thread per ACT_ENC_BATCH
+// spend verification, stage 1b: encode the 256 half-commitments of a proof.  One thread per ACT_ENC_BATCH (64)
 // consecutive points: Montgomery-batched inversion, then the square-root-free double-and-encode.
 // Writes items 133 .. 388.
 // =============================================================================================================
-#define ACT_ENC_BATCH 16
+// points per thread = points per field inversion.  Measured at 131 072 proofs (profiles/r02j_variants_enc_sign.txt): 16 -> 13.73 ms,
+// 32 -> 12.23 ms, 64 -> 11.81 ms in the encode kernel.
+#ifndef ACT_ENC_BATCH
+#define ACT_ENC_BATCH 64
+#endif
 // pts = points per proof in cpts (256 for the verifier: items 133..388; 384 for the prover: items 5..388), item0 = first item
 ACT_FN void spend_encode_thread(const act_ctx* C, size_t p, int part, const u32* cpts, u32* items, int pts = 2 * ACT_L, int item0 = 133) {
     (void)C;
