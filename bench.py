@@ -40,12 +40,12 @@ UNIT = "proofs/s"
 #       (round 1's window form: 1506 S + 2583 M = 2.522e5 -> 3.23e7; the constant follows the algorithm that runs)
 #       = the EXECUTED IMAD.WIDE lane count ncu reports for the kernel (3.0396e7 per proof, profiles/r02e_spend_range.txt)
 #   the other stages: the executed IMAD.WIDE(.X) lane counts of one ncu capture each at the product launch shape
-#   (profiles/r02f_*.txt): encode 6.81e5 (5.37e5 after r02j's 64-point batches, profiles/r02k_spend_encode_kernel.txt), head 7.43e5, sign 3.40e5 per proof, issue 5.37e5 per request.  (Round 1's hand counts --
+#   (profiles/r02f_*.txt): encode 5.40e5 (profiles/r02k_spend_encode_kernel.txt; 6.81e5 before r02j's 64-point batches), head 7.43e5, sign 3.40e5 per proof, issue 5.37e5 per request.  (Round 1's hand counts --
 #   7.1e5 / 8.2e5 / 3.9e5 / 6.0e5 -- were 4-13 % too high; the constants below are what the kernels execute.)
 LIMB_MACS_PER_SPEND_RANGE = 128 * (1266 * 44 + 2525 * 72)      # 3.040e7
 LIMB_MACS_PER_SPEND_HEAD = 7.43e5
 LIMB_MACS_PER_SPEND_SIGN = 3.40e5
-LIMB_MACS_PER_SPEND_ENCODE = 5.37e5     # 6.81e5 executed at 16 points per inversion (r02f); 64 per inversion since r02j: - 256 x (254 S + 11 M) x (1/16 - 1/64)
+LIMB_MACS_PER_SPEND_ENCODE = 5.40e5     # executed at 64 points per inversion (profiles/r02k_spend_encode_kernel.txt); 6.81e5 at 16 per inversion (r02f)
 LIMB_MACS_PER_SPEND = LIMB_MACS_PER_SPEND_RANGE + LIMB_MACS_PER_SPEND_ENCODE + LIMB_MACS_PER_SPEND_HEAD + LIMB_MACS_PER_SPEND_SIGN
 LIMB_MACS_PER_ISSUE = 5.37e5
 MIXED_N_1GPU = 1 << 22               # BASELINE configs[4]: 4M requests on one GPU

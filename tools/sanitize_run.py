@@ -26,4 +26,17 @@ with act.Engine(params, act.PrivateKey.from_secret(ctx.x)) as eng:
     stream = np.zeros(128 * n, np.uint8)
     eng.batch_verify_spend_and_refund_seq(proofs, stream)
     eng.batch_issue_seq(req, cs, stream)
+    # round 2: two-pass forms, the screened call, a chunk-crossing batch with ramp chunks, and a two-replica engine
+    nul2, st2, kp = eng.batch_spend_verify(proofs)
+    eng.batch_refund_sign(kp, st2, stream)
+    eng.batch_issue_sign(req, cs, eng.batch_issue_verify(req), stream)
+    eng.batch_verify_spend_and_refund_screened(proofs, rnd, seen=nul[:64])
+    eng.set_spend_chunk(4096)
+    m = 4096 + 700
+    u = len(proofs) // corpus.PROOF_BYTES
+    idx = np.arange(m) % u
+    eng.batch_verify_spend_and_refund(proofs.reshape(u, -1)[idx].reshape(-1).copy(), rnd.reshape(u, -1)[idx].reshape(-1).copy())
+with act.Engine(params, act.PrivateKey.from_secret(ctx.x), devices=[0, 0]) as meng:
+    meng.batch_verify_spend_and_refund_screened(proofs, rnd)
+    meng.batch_issue(req, cs, irnd)
 print("sanitize_run ok", s.tolist(), ist.tolist())
