@@ -537,48 +537,12 @@ def main():
     barrier()
     e2e_issue_s = time.perf_counter() - t0
 
-    # ---- single-process multi-device leg (N > 1): rank 0 alone drives every GPU of the box through ONE C-ABI handle
-    # (act_engine_create_multi + act_batch_verify_spend_and_refund_screened: shards over per-device replicas, NVLink gather of
-    # status + nullifiers to replica 0, replay screen), the other ranks wait on a host-side barrier with their GPUs idle ----
-    multi_abi = None
-    if world > 1 and not args.no_multi_abi:
-        nm = max(1, min(262144, n // world))     # disjoint windows of rank 0's unique proofs: no nullifier repeats
-        torch.cuda.synchronize()
-        dist.barrier(group=cpu_group)
-        if rank == 0:
-            try:
-                tiles = world
-                mp_ = torch.empty(tiles * nm * PROOF_BYTES, dtype=torch.uint8, pin_memory=True)
-                mr_ = torch.empty(tiles * nm * 128, dtype=torch.uint8, pin_memory=True)
-                for g in range(tiles):   # rank 0's own unique proofs, a different window per GPU shard
-                    lo = g * nm
-                    mp_[g * nm * PROOF_BYTES:(g + 1) * nm * PROOF_BYTES].copy_(h_proofs[lo * PROOF_BYTES:(lo + nm) * PROOF_BYTES])
-                    mr_[g * nm * 128:(g + 1) * nm * 128].copy_(h_rnd[lo * 128:(lo + nm) * 128])
-                tot = tiles * nm
-                m_ref = torch.empty(tot * 128, dtype=torch.uint8, pin_memory=True); m_nul = torch.empty(tot * 32, dtype=torch.uint8, pin_memory=True)
-                m_st = torch.empty(tot, dtype=torch.uint8, pin_memory=True)
-                with act.Engine(params, key, devices=list(range(world))) as meng:
-                    def mstep():
-                        meng.batch_verify_spend_and_refund_screened_ptr(tot, mp_.data_ptr(), mr_.data_ptr(), 0, None, m_ref.data_ptr(), m_nul.data_ptr(), m_st.data_ptr())
-                    mstep()
-                    t0 = time.perf_counter()
-                    msteps = 3
-                    for _ in range(msteps):
-                        mstep()
-                    m_s = time.perf_counter() - t0
-                    stv = m_st.numpy()
-                    multi_abi = {"value": tot * msteps / m_s, "unit": UNIT, "n": tot, "steps": msteps, "n_gpus": world,
-                                 "api": "act_engine_create_multi + act_batch_verify_spend_and_refund_screened: one process, one handle, pinned host buffers, "
-                                        "shards over per-device replicas, cudaMemcpyPeerAsync gather of status + nullifiers to replica 0, replay screen",
-                                 "accepted": int((stv == 0).sum()), "flagged_replays": int((stv == 3).sum()),
-                                 "first_shard_equals_rank0_refunds": bool((m_ref[:nm * 128].numpy() == h_ref[:nm * 128].numpy()).all())}
-                    assert multi_abi["first_shard_equals_rank0_refunds"], "multi-device leg differs from the per-rank leg"
-                    assert int((stv == 0).sum()) == tot, "multi-device leg: a valid unique proof was rejected or flagged"
-                del mp_, mr_, m_ref, m_nul, m_st
-            except Exception as ex:
-                multi_abi = {"unavailable": repr(ex)}
-        dist.barrier(group=cpu_group)
-
+    nm = max(1, min(262144, n // world))     # per-GPU shard of the multi-device leg: disjoint windows of rank 0's unique proofs
+    m_keep = None
+    if world > 1 and not args.no_multi_abi and rank == 0:
+        mk_p = torch.empty(world * nm * PROOF_BYTES, dtype=torch.uint8, pin_memory=True); mk_p.copy_(h_proofs[:world * nm * PROOF_BYTES])
+        mk_r = torch.empty(world * nm * 128, dtype=torch.uint8, pin_memory=True); mk_r.copy_(h_rnd[:world * nm * 128])
+        m_keep = (mk_p, mk_r, h_ref[:nm * 128].clone())
     del h_proofs
     torch.cuda.empty_cache()
 
@@ -726,6 +690,55 @@ def main():
     elif world > 1 and per == n:
         strong = {"note": f"at N = {world} the weak run IS the {STRONG_TOTAL}-proof batch of configs[3] ({n} per GPU)"}
 
+    # ---- single-process multi-device leg (N > 1), LAST: rank 0 alone drives every GPU of the box through ONE C-ABI handle
+    # (act_engine_create_multi + act_batch_verify_spend_and_refund_screened: shards over per-device replicas, NVLink gather of
+    # status + nullifiers to replica 0, replay screen).  The other ranks have nothing left to do and EXIT (code 0) first: an idle
+    # process that still holds a CUDA context on a GPU makes the driver time-slice it against rank 0's replica there (measured at
+    # N = 4: steps between 1.29 s and 2.08 s with the idle ranks alive, 1.286 s steady from a lone process,
+    # profiles/r02m_multi_abi.txt) ----
+    multi_abi = None
+    if world > 1 and not args.no_multi_abi:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        dist.destroy_process_group()          # every rank: no communicator is left that could notice a peer leaving
+        if rank != 0:
+            sys.stderr.flush()
+            os._exit(0)
+        eng.close()
+        del d_ref, d_nul, d_st, d_rnd, d_tokens
+        torch.cuda.empty_cache()
+        time.sleep(5.0)                       # the exited ranks' contexts are torn down by the driver
+        if rank == 0:
+            try:
+                mp_, mr_, ref0 = m_keep
+                tot = world * nm
+                m_ref = torch.empty(tot * 128, dtype=torch.uint8, pin_memory=True); m_nul = torch.empty(tot * 32, dtype=torch.uint8, pin_memory=True)
+                m_st = torch.empty(tot, dtype=torch.uint8, pin_memory=True)
+                with act.Engine(params, key, devices=list(range(world))) as meng:
+                    def mstep():
+                        meng.batch_verify_spend_and_refund_screened_ptr(tot, mp_.data_ptr(), mr_.data_ptr(), 0, None, m_ref.data_ptr(), m_nul.data_ptr(), m_st.data_ptr())
+                    mstep(); mstep()
+                    msteps = 5
+                    step_s = []
+                    for _ in range(msteps):
+                        t0 = time.perf_counter()
+                        mstep()
+                        step_s.append(time.perf_counter() - t0)
+                    m_s = sum(step_s)
+                    stv = m_st.numpy()
+                    multi_abi = {"value": tot * msteps / m_s, "unit": UNIT, "n": tot, "steps": msteps, "n_gpus": world, "step_s": [round(t, 4) for t in step_s],
+                                 "api": "act_engine_create_multi + act_batch_verify_spend_and_refund_screened: one process, one handle, pinned host buffers, "
+                                        "shards over per-device replicas, cudaMemcpyPeerAsync gather of status + nullifiers to replica 0, replay screen",
+                                 "accepted": int((stv == 0).sum()), "flagged_replays": int((stv == 3).sum()),
+                                 "first_shard_equals_rank0_refunds": bool((m_ref[:nm * 128].numpy() == ref0.numpy()).all()),
+                                 "note": "run last, after the other ranks have exited; tools/multi_abi_bench.py measures the same call from a "
+                                         "lone process (profiles/r02m_multi_abi.txt)"}
+                    assert multi_abi["first_shard_equals_rank0_refunds"], "multi-device leg differs from the per-rank leg"
+                    assert int((stv == 0).sum()) == tot, "multi-device leg: a valid unique proof was rejected or flagged"
+                del mp_, mr_, m_ref, m_nul, m_st
+            except Exception as ex:
+                multi_abi = {"unavailable": repr(ex)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(ctx, base, reqs, os.cpu_count() or 1)
@@ -760,6 +773,9 @@ def main():
         }
         real_stdout.write(json.dumps(out) + "\n")
         real_stdout.flush()
+    if world > 1 and not args.no_multi_abi:
+        sys.stderr.flush()
+        os._exit(0)                           # process group already destroyed, engine closed
     eng.close()
     if world > 1:
         dist.destroy_process_group()

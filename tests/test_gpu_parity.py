@@ -623,3 +623,39 @@ def test_screened_batch_call(act, engine, octx, base):
             ref, nul, st = eng.batch_verify_spend_and_refund_screened(P, R, seen=seen.reshape(-1))
             assert (st == e_st).all()
             assert (ref.reshape(n, -1) == e_ref).all() and (nul.reshape(n, -1) == e_nul).all()
+
+
+def test_differential_fuzz_against_the_oracle(engine, octx, base):
+    """prop_invalid_proofs_rejected (src/tests.rs:1681-1713) turned into a differential fuzz: 600 records with 1-3 random bit flips
+    anywhere in the 16 832 bytes (points, scalars, any field), 400 requests likewise, plus whole-field random replacements --
+    status, refund / response and nullifier bytes equal the oracle's on every record, whatever the oracle says."""
+    rs = np.random.RandomState(20261017)
+    u = len(base["proofs"]) // corpus.PROOF_BYTES
+    n = 600
+    P = base["proofs"].reshape(u, -1)[rs.randint(0, u, n)].copy(); R = base["rnd"].reshape(u, -1)[rs.randint(0, u, n)].copy()
+    for i in range(n):
+        if i % 5 == 4:      # a whole 32-byte item replaced by random bytes (a random point encoding decodes about one time in four)
+            item = rs.randint(0, 526)
+            P[i, 32 * item:32 * item + 32] = rs.randint(0, 256, 32)
+        else:
+            for _ in range(1 + i % 3):
+                b = rs.randint(0, corpus.PROOF_BYTES * 8)
+                P[i, b // 8] ^= 1 << (b % 8)
+    P = P.reshape(-1); R = R.reshape(-1)
+    ref, nul, st = engine.batch_verify_spend_and_refund(P, R)
+    o_ref, o_nul, o_st, _ = octx.batch_refund(P, R, threads=8)
+    assert st.tolist() == o_st.tolist()
+    assert (ref == o_ref).all() and (nul == o_nul).all()
+    assert {7, 0x81} <= set(st.tolist())
+    m = 400
+    Q = base["req"].reshape(u, -1)[rs.randint(0, u, m)].copy(); C = base["cs"].reshape(u, -1)[rs.randint(0, u, m)].copy()
+    IR = base["rnd"].reshape(u, -1)[rs.randint(0, u, m)].copy()
+    for i in range(m):
+        b = rs.randint(0, 128 * 8)
+        Q[i, b // 8] ^= 1 << (b % 8)
+        if i % 7 == 0:
+            C[i] = rs.randint(0, 256, 32)          # any 32 bytes are a credit amount (reduced mod l)
+    Q = Q.reshape(-1); C = C.reshape(-1); IR = IR.reshape(-1)
+    resp, ist = engine.batch_issue(Q, C, IR)
+    o_resp, o_ist, _ = octx.batch_issue(Q, C, IR, threads=8)
+    assert ist.tolist() == o_ist.tolist() and (resp == o_resp).all()

@@ -292,6 +292,38 @@ def test_whole_mutation_corpus_oracle_vs_independent_stack(octx):
     assert set(got) == {0, 4, 0x81}
 
 
+@pytest.mark.skipif(not R.available(), reason="libsodium with ristretto255 not found")
+def test_differential_fuzz_oracle_vs_independent_stack(octx):
+    """Random bit flips and whole-item replacements anywhere in SpendProof and IssuanceRequest records: the oracle and the
+    independent stack agree on status and output bytes for every record (the GPU suite runs the same fuzz, engine vs oracle)."""
+    _XS.update(H=[octx.h[0:32], octx.h[32:64], octx.h[64:96]], x=int.from_bytes(octx.x, "little"), w=octx.w)
+    PB = O.PROOF_BYTES
+    base = corpus.gen_valid(octx, 8, seed=b"fuzz-xcheck", threads=8)
+    rs = np.random.RandomState(77)
+    n = 96
+    P = base["proofs"].reshape(8, -1)[rs.randint(0, 8, n)].copy(); Rn = base["rnd"].reshape(8, -1)[rs.randint(0, 8, n)].copy()
+    for i in range(n):
+        if i % 4 == 3:
+            item = rs.randint(0, 526); P[i, 32 * item:32 * item + 32] = rs.randint(0, 256, 32)
+        elif i % 4:
+            b = rs.randint(0, PB * 8); P[i, b // 8] ^= 1 << (b % 8)
+    o_ref, o_nul, o_st, _ = octx.batch_refund(P.reshape(-1), Rn.reshape(-1), threads=8)
+    got = _pool_map(_x_refund, [(P[i].tobytes(), Rn[i].tobytes()) for i in range(n)])
+    for i, (st, ref, nul) in enumerate(got):
+        assert st == o_st[i] and ref == o_ref[128 * i:128 * i + 128].tobytes() and nul == o_nul[32 * i:32 * i + 32].tobytes(), i
+    assert {0, 7, 0x81} <= set(o_st.tolist())
+    Q = base["req"].reshape(8, -1)[rs.randint(0, 8, n)].copy(); C = base["cs"].reshape(8, -1)[rs.randint(0, 8, n)].copy()
+    for i in range(n):
+        if i % 3:
+            b = rs.randint(0, 128 * 8); Q[i, b // 8] ^= 1 << (b % 8)
+        if i % 5 == 0:
+            C[i] = rs.randint(0, 256, 32)
+    o_resp, o_ist, _ = octx.batch_issue(Q.reshape(-1), C.reshape(-1), Rn.reshape(-1), threads=8)
+    got = _pool_map(_x_issue, [(Q[i].tobytes(), C[i].tobytes(), Rn[i].tobytes()) for i in range(n)])
+    for i, (st, resp) in enumerate(got):
+        assert st == o_ist[i] and resp == o_resp[160 * i:160 * i + 160].tobytes(), i
+
+
 def test_token_lifecycles(octx):
     """The reference's scenario tests (sequential spends, exact balance, zero spend, zero-credit token, one-credit
     exhaustion, 2^120 and 2^128-1 credit tokens, overspend; src/tests.rs:210-426,642-689,876-1059) as multi-generation
