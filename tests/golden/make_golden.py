@@ -6,7 +6,10 @@
   corpus_small.npz   a small adversarial batch (valid + mutated requests/proofs) with the oracle's outputs, so the GPU
                      parity tests can also be checked against committed bytes.
 
-Run from the repo root:  python tests/golden/make_golden.py
+  corpus_checks.npz  (round 2) tampered IssuanceResponses / Refunds for the client-side checks and proofs made from tampered tokens,
+                     with statuses and outputs computed by the independent stack and asserted equal to the oracle's.
+
+Run from the repo root:  python tests/golden/make_golden.py [trip] [corpus_small] [corpus_checks]
 """
 import hashlib
 import json
@@ -62,6 +65,34 @@ def corpus_small():
     print("corpus_small.npz", st_i.tolist(), st.tolist())
 
 
+def corpus_checks():
+    """Round 2: the tamper classes of the client-side checks (rows a3, a4) and the tampered-token proofs, with statuses computed by
+    the INDEPENDENT stack (tests/refstack.py record-level front ends) and asserted equal to the oracle's."""
+    ctx = corpus.make_ctx(corpus.TEST_PARAMS)
+    H = [ctx.h[0:32], ctx.h[32:64], ctx.h[64:96]]
+    x = int.from_bytes(ctx.x, "little")
+    base = corpus.gen_valid(ctx, 20, seed=b"golden-checks", threads=4)
+    K, rs, _, _ = corpus.mutate_responses(base)
+    st_ic = np.array([R.issuance_check_record(H, ctx.w, K[32 * i:32 * i + 32], rs[160 * i:160 * i + 160]) for i in range(20)], np.uint8)
+    assert st_ic.tolist() == ctx.batch_issuance_check(K, rs, threads=4)[0].tolist()
+    ref, nul, st, _ = ctx.batch_refund(base["proofs"], base["rnd"], threads=4)
+    assert (st == 0).all()
+    com = base["proofs"].reshape(20, -1)[:, 128:128 + 4096].copy().reshape(-1)
+    c2, r2, _, _ = corpus.mutate_refunds(com, ref)
+    st_rc = np.array([R.refund_check_record(H, ctx.w, c2[4096 * i:4096 * i + 4096], r2[128 * i:128 * i + 128]) for i in range(20)], np.uint8)
+    assert st_rc.tolist() == ctx.batch_refund_check(c2, r2, threads=4)[0].tolist()
+    t = corpus.tampered_token_proofs(ctx, 10)
+    outs = [R.refund_record(H, x, ctx.w, t["proofs"][O.PROOF_BYTES * i:O.PROOF_BYTES * (i + 1)], t["rnd"][128 * i:128 * i + 128]) for i in range(10)]
+    o_ref, o_nul, o_st, _ = ctx.batch_refund(t["proofs"], t["rnd"], threads=4)
+    assert [o[0] for o in outs] == o_st.tolist() and b"".join(o[1] for o in outs) == o_ref.tobytes() and b"".join(o[2] for o in outs) == o_nul.tobytes()
+    np.savez_compressed(os.path.join(HERE, "corpus_checks.npz"), h=np.frombuffer(ctx.h, np.uint8), x=np.frombuffer(ctx.x, np.uint8),
+                        w=np.frombuffer(ctx.w, np.uint8), K=K, responses=rs, status_issuance_check=st_ic, com=c2, refunds=r2,
+                        status_refund_check=st_rc, token_proofs=t["proofs"], token_rnd=t["rnd"], token_status=np.array([o[0] for o in outs], np.uint8),
+                        token_refunds=np.frombuffer(b"".join(o[1] for o in outs), np.uint8), token_nullifiers=np.frombuffer(b"".join(o[2] for o in outs), np.uint8))
+    print("corpus_checks.npz", st_ic.tolist(), st_rc.tolist(), [o[0] for o in outs])
+
+
 if __name__ == "__main__":
-    trip()
-    corpus_small()
+    which = sys.argv[1:] or ["trip", "corpus_small", "corpus_checks"]
+    for w in which:
+        {"trip": trip, "corpus_small": corpus_small, "corpus_checks": corpus_checks}[w]()

@@ -199,6 +199,13 @@ def test_golden_trip_and_corpus_on_gpu(act):
         assert (st == c["status_issue"]).all() and (resp == c["resp"]).all()
         ref, nul, st = eng.batch_verify_spend_and_refund(c["proofs"], c["rnd"])
         assert (st == c["status"]).all() and (ref == c["refunds"]).all() and (nul == c["nullifiers"]).all()
+        # round-2 fixture: tampered responses / refunds for the client-side checks and proofs made from tampered tokens (same key)
+        k = np.load(os.path.join(here, "golden", "corpus_checks.npz"))
+        assert k["h"].tobytes() == c["h"].tobytes() and k["x"].tobytes() == c["x"].tobytes()
+        assert (eng.batch_issuance_check(k["K"], k["responses"]) == k["status_issuance_check"]).all()
+        assert (eng.batch_refund_check(k["com"], k["refunds"]) == k["status_refund_check"]).all()
+        ref, nul, st = eng.batch_verify_spend_and_refund(k["token_proofs"], k["token_rnd"])
+        assert (st == k["token_status"]).all() and (ref == k["token_refunds"]).all() and (nul == k["token_nullifiers"]).all()
 
 
 def test_ragged_sizes_around_the_resident_grid(engine, octx, base):

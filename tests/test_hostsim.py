@@ -180,6 +180,17 @@ def test_golden_corpus_small():
     assert (st == g["status"]).all() and (ref == g["refunds"]).all() and (nul == g["nullifiers"]).all()
 
 
+def test_golden_corpus_checks():
+    """tests/golden/corpus_checks.npz (statuses and outputs computed by the independent stack): the tamper classes of the two
+    client-side checks and the proofs made from tampered tokens, through the host build of the device code."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corpus_checks.npz"))
+    hs = HS.Ctx(g["h"].tobytes(), g["x"].tobytes(), g["w"].tobytes())
+    assert (hs.issuance_check(g["K"], g["responses"]) == g["status_issuance_check"]).all()
+    assert (hs.refund_check(g["com"], g["refunds"]) == g["status_refund_check"]).all()
+    ref, nul, st = hs.refund(g["token_proofs"], g["token_rnd"])
+    assert (st == g["token_status"]).all() and (ref == g["token_refunds"]).all() and (nul == g["token_nullifiers"]).all()
+
+
 def test_batched_double_and_encode_stage_with_identity_points():
     """Stage 1b (Montgomery-batched, square-root-free encode of 2P) vs the oracle's encode(2*P), including identity
     points inside a batch (e*g*f*h = 0 must not poison the other 15 points of the batch)."""

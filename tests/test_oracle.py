@@ -324,6 +324,17 @@ def test_differential_fuzz_oracle_vs_independent_stack(octx):
         assert st == o_ist[i] and resp == o_resp[160 * i:160 * i + 160].tobytes(), i
 
 
+def test_golden_corpus_checks_on_the_oracle():
+    """The committed round-2 fixture (independent-stack statuses and outputs for tampered responses, refunds and tokens)."""
+    g = np.load(os.path.join(HERE, "golden", "corpus_checks.npz"))
+    ctx = O.Ctx(g["h"].tobytes(), g["x"].tobytes(), g["w"].tobytes())
+    assert (ctx.batch_issuance_check(g["K"], g["responses"], threads=4)[0] == g["status_issuance_check"]).all()
+    assert (ctx.batch_refund_check(g["com"], g["refunds"], threads=4)[0] == g["status_refund_check"]).all()
+    ref, nul, st, _ = ctx.batch_refund(g["token_proofs"], g["token_rnd"], threads=4)
+    assert (st == g["token_status"]).all() and (ref == g["token_refunds"]).all() and (nul == g["token_nullifiers"]).all()
+    assert set(g["status_issuance_check"].tolist()) == {0, 2, 0x81} and set(g["status_refund_check"].tolist()) == {0, 4, 0x81}
+
+
 def test_token_lifecycles(octx):
     """The reference's scenario tests (sequential spends, exact balance, zero spend, zero-credit token, one-credit
     exhaustion, 2^120 and 2^128-1 credit tokens, overspend; src/tests.rs:210-426,642-689,876-1059) as multi-generation
