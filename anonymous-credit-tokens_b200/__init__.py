@@ -197,7 +197,11 @@ class Params:
 
 
 class PrivateKey:
-    """Issuer key (reference `PrivateKey`, src/lib.rs:160-167): secret scalar x and public W = G*x (encoded)."""
+    """Issuer key (reference `PrivateKey`, src/lib.rs:160-167): secret scalar x and public W = G*x (encoded).
+
+    This Python mirror exists for the tests and the bench: it keeps `x` in an immutable `bytes` object, which cannot be
+    zeroised (the reference's PrivateKey is ZeroizeOnDrop).  A production host holds the key in memory it controls and passes a
+    pointer to act_engine_create, which wipes its own staging copy; the device copy is zeroised by act_engine_destroy."""
 
     def __init__(self, x, w):
         self.x, self.w = bytes(x), bytes(w)

@@ -12,6 +12,13 @@
  *   act_batch_issuance_check[_dev]     = n x PreIssuance::to_credit_token     src/lib.rs:528-562 (verification half)
  *   act_batch_refund_check[_dev]       = n x PreRefund::to_credit_token       src/lib.rs:1217-1253 (verification half)
  *   act_pack_* / act_encode_*          = from_cbor / to_cbor                  src/cbor.rs:94-465
+ *   act_batch_issue_verify + _sign,
+ *   act_batch_spend_verify + act_batch_refund_sign
+ *                                      = the same calls split where the reference draws from its RNG
+ *                                        (after verification: src/lib.rs:638-643, 842-846), for hosts that own ONE RNG
+ *   act_engine_create_multi            = one handle over several GPUs; host-buffer calls shard by request
+ *   act_batch_verify_spend_and_refund_screened
+ *                                      = refund() behind the caller's nullifier check (examples/act.rs:60-77) for a slice
  *
  * Records hold WIRE bytes: points are 32-byte compressed ristretto255 encodings (validated on the
  * device exactly like CompressedRistretto::decompress, src/cbor.rs:62-77) and scalars are 32-byte
