@@ -336,6 +336,9 @@ ACT_FN ge bucket_load(vb_table* t, u32 idx) {
     load8_rw(p.X.v, q); load8_rw(p.Y.v, q + 8); load8_rw(p.Z.v, q + 16); load8_rw(p.T.v, q + 24);
     return p;
 }
+#ifndef ACT_BUCKET_SKIP0
+#define ACT_BUCKET_SKIP0 0
+#endif
 ACT_FN void vb_pair_buckets_fill(const ge& P, const sc& s0, const sc& s1, vb_table* t) {
     sc b0 = sc_bias<4>(s0), b1 = sc_bias<4>(s1);
     {
@@ -347,6 +350,20 @@ ACT_FN void vb_pair_buckets_fill(const ge& P, const sc& s0, const sc& s1, vb_tab
         ge_cached Qc = ge_to_cached(Q);
         ACT_NOUNROLL for (int r = 0; r < 2; r++) {
             int d = sc_digit<4>(r ? b1 : b0, i);
+#if ACT_BUCKET_SKIP0
+            // a zero digit adds into a copy of bucket 1 that is never stored: every lane still adds at every step (lock-step), but
+            // bucket 0 does not exist and one store in sixteen is predicated off
+            u32 ad = (u32)(d < 0 ? -d : d);
+            u32 idx = 9u * (u32)r + (ad ? ad : 1u);
+            if (i + 1 < 64 || r == 0) {
+                int dn = r ? sc_digit<4>(b0, i + 1) : sc_digit<4>(b1, i);
+                u32 an = (u32)(dn < 0 ? -dn : dn);
+                prefetch_line(bucket_ptr(t, 9u * (u32)(r ^ 1) + (an ? an : 1u)));
+            }
+            ge B = bucket_load(t, idx);
+            B = ge_add_cached_u<true>(B, Qc, d < 0 ? 0u : 1u, true);
+            if (ad) bucket_store(t, idx, B);
+#else
             u32 idx = 9u * (u32)r + (u32)(d < 0 ? -d : d);
             if (i + 1 < 64 || r == 0) {   // the bucket of the next addition travels to L1 while this one runs
                 int dn = r ? sc_digit<4>(b0, i + 1) : sc_digit<4>(b1, i);
@@ -355,6 +372,7 @@ ACT_FN void vb_pair_buckets_fill(const ge& P, const sc& s0, const sc& s1, vb_tab
             ge B = bucket_load(t, idx);
             B = ge_add_cached_u<true>(B, Qc, d < 0 ? 0u : 1u, true);      // bucket += -sign(d) Q_i
             bucket_store(t, idx, B);
+#endif
         }
         if (i + 1 < 64) {
             ACT_NOUNROLL for (int k = 0; k < 4; k++) Q = ge_dbl_u<true>(Q, k == 3);
