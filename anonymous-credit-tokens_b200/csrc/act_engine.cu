@@ -814,12 +814,21 @@ extern "C" int act_selftest(int device) {
 }
 
 static inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+// device-buffer entry points move records with 16-byte vector accesses: a misaligned pointer would fault inside a kernel
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+#define NEED_ALIGNED(what, ...)                                                                                     \
+    do {                                                                                                            \
+        const void* ps_[] = {__VA_ARGS__};                                                                          \
+        for (const void* p_ : ps_) if (p_ && !aligned16(p_)) return fail_msg(what ": device buffers must be 16-byte aligned"); \
+    } while (0)
 
 // ---- device-buffer entry points ----
 extern "C" int act_batch_issue_dev(act_engine* e, size_t n, const void* req, const void* c, const void* rnd, void* resp, void* status, void* stream) {
     if (!e) return fail_msg("null engine");
     NOT_MULTI(e, "act_batch_issue_dev");
     if (n == 0) return 0;
+    if (!req || !c || !rnd || !resp || !status) return fail_msg("act_batch_issue_dev: null buffer");
+    NEED_ALIGNED("act_batch_issue_dev", req, c, rnd, resp);
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
     LAUNCH(e, K_ISSUE, st, (issue_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)req, (const u32*)c, (const u32*)rnd, (u32*)resp, (u8*)status)));
@@ -830,6 +839,8 @@ extern "C" int act_batch_issuance_check_dev(act_engine* e, size_t n, const void*
     if (!e) return fail_msg("null engine");
     NOT_MULTI(e, "act_batch_issuance_check_dev");
     if (n == 0) return 0;
+    if (!K || !resp || !status) return fail_msg("act_batch_issuance_check_dev: null buffer");
+    NEED_ALIGNED("act_batch_issuance_check_dev", K, resp);
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
     LAUNCH(e, K_ISSUANCE_CHECK, st, (issuance_check_kernel<<<nblocks(n, ACT_ISSUE_BLOCK), ACT_ISSUE_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)K, (const u32*)resp, (u8*)status)));
@@ -840,6 +851,8 @@ extern "C" int act_batch_refund_check_dev(act_engine* e, size_t n, const void* c
     if (!e) return fail_msg("null engine");
     NOT_MULTI(e, "act_batch_refund_check_dev");
     if (n == 0) return 0;
+    if (!com || !refund || !status) return fail_msg("act_batch_refund_check_dev: null buffer");
+    NEED_ALIGNED("act_batch_refund_check_dev", com, refund);
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream[0];
     LAUNCH(e, K_REFUND_CHECK, st, (refund_check_kernel<<<nblocks(n, ACT_HEAD_BLOCK), ACT_HEAD_BLOCK, 0, st>>>(e->d_ctx, n, (const u32*)com, (const u32*)refund, (u8*)status)));
@@ -880,6 +893,7 @@ extern "C" int act_batch_verify_spend_and_refund_dev(act_engine* e, size_t n, co
     NOT_MULTI(e, "act_batch_verify_spend_and_refund_dev");
     if (n == 0) return 0;
     if (!proofs || !rnd || !refunds || !nullifiers || !status) return fail_msg("act_batch_verify_spend_and_refund_dev: null buffer");
+    NEED_ALIGNED("act_batch_verify_spend_and_refund_dev", proofs, rnd, refunds, nullifiers);
     CK(cudaSetDevice(e->device));
     cudaStream_t user = stream ? (cudaStream_t)stream : e->stream[0];
     const size_t ACT_SPEND_CHUNK_RT = e->spend_chunk;

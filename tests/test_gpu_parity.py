@@ -666,3 +666,17 @@ def test_differential_fuzz_against_the_oracle(engine, octx, base):
     resp, ist = engine.batch_issue(Q, C, IR)
     o_resp, o_ist, _ = octx.batch_issue(Q, C, IR, threads=8)
     assert ist.tolist() == o_ist.tolist() and (resp == o_resp).all()
+
+
+def test_device_entry_points_reject_misaligned_and_null_buffers(act, engine):
+    """The _dev calls move records with 16-byte vector accesses: a misaligned or null device pointer is refused up front
+    (a whole-call error), never dereferenced."""
+    import torch
+    buf = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
+    p = buf.data_ptr()
+    with pytest.raises(act.ActError, match="16-byte aligned"):
+        engine.batch_issue_dev(1, p + 4, p + 1024, p + 2048, p + 4096, p + 8192)
+    with pytest.raises(act.ActError, match="16-byte aligned"):
+        engine.batch_verify_spend_and_refund_dev(1, p, p + 32768 + 8, p + 40000 - 40000 % 16, p + 50000 - 50000 % 16, p + 60000)
+    with pytest.raises(act.ActError, match="null buffer"):
+        engine.batch_issue_dev(1, p, None, p + 2048, p + 4096, p + 8192)
