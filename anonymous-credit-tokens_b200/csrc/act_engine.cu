@@ -1022,7 +1022,7 @@ extern "C" int act_batch_issue(act_engine* e, size_t n, const uint8_t* req, cons
     host_io h = {{req, c, rnd}, {128, 32, 128}, {resp, nullptr, status}, {160, 0, 1}, 2};
     return run_chunked(e, n, ACT_SMALL_CHUNK, h, [&](int, cudaStream_t st, size_t m, io_slot& io) {
         return act_batch_issue_dev(e, m, io.in0, io.in1, io.in2, io.out0, io.st, st);
-    });
+    }, true);
 }
 extern "C" int act_batch_issuance_check(act_engine* e, size_t n, const uint8_t* K, const uint8_t* resp, uint8_t* status) {
     if (!e) return fail_msg("null engine");
