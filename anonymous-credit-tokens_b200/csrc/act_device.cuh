@@ -267,6 +267,25 @@ ACT_FN ge vb_mul_multi(const vb_table* t, const sc* s, const bool* negate) {
     return acc;
 }
 ACT_FN ge vb_mul(const vb_table* t, const sc& s, bool negate) { return vb_mul_multi<1>(t, &s, &negate); }
+// (negate ? -s : s) * P for ONE public scalar: the entry of the coming addition is prefetched before the four doublings, the point
+// operations are the public-data forms, and T is only produced by the last addition (a doubling does not read it).  Same group
+// element as vb_mul.  (Measured for issue_kernel, profiles/r02y_variants_issue_pub.txt: +0.7 %; moving the table from the stack to a
+// per-resident-thread global scratch needs a persistent grid, whose static grid-stride loop lost 6 % to uneven warp progress.)
+ACT_FN ge vb_mul_pub(const vb_table* t, const sc& s, bool negate) {
+    sc b = sc_bias<4>(s);
+    ge a = ge_identity();
+    ACT_NOUNROLL for (int i = 63; i >= 0; i--) {
+        int d = sc_digit<4>(b, i);
+        u32 ad = (u32)(d < 0 ? -d : d);
+        prefetch_line(&t->e[ad]);
+        if (i != 63) {
+            ACT_NOUNROLL for (int k = 0; k < 4; k++) a = ge_dbl_u<true>(a, k == 3);
+        }
+        u32 neg = ((d < 0) ? 1u : 0u) ^ (negate ? 1u : 0u);
+        a = ge_add_cached_u<true>(a, tab_load(t, ad), neg, i == 0);
+    }
+    return a;
+}
 
 // Two public scalars on ONE base with separate results (the range-proof pair com_j*gamma0_j, com_j*gamma01_j): the
 // base's doubling chain is shared.  With P_k = 2^(256k/M) P precomputed once (256(M-1)/M doublings, M window tables),
@@ -541,6 +560,9 @@ ACT_NOINLINE void bbs_sign_(const act_ctx* C, const ge* X_A, const u32* rnd, int
 // mode ACT_MODE_SIGN: status[i] is given (by a VERIFY pass); accepted requests are signed with the RNG bytes at
 //      rnd + 32 * rnd_index[i] -- the position a sequential loop over ONE shared RNG would have reached (the reference
 //      draws e, alpha only after a request verifies, src/lib.rs:638-643).
+#ifndef ACT_ISSUE_PUB
+#define ACT_ISSUE_PUB 1
+#endif
 #define ACT_MODE_FULL 0
 #define ACT_MODE_VERIFY 1
 #define ACT_MODE_SIGN 2
@@ -560,7 +582,11 @@ ACT_FN void issue_thread(const act_ctx* C, size_t i, const u32* req, const u32* 
     // K1 = h2*k_bar + h3*r_bar - K*gamma                                                     (:629-630)
     vb_table tk;
     vb_table_build(&tk, K);
+#if ACT_ISSUE_PUB
+    ge K1 = vb_mul_pub(&tk, gamma, true);     // K and gamma are public: variable-time forms, T only on the last addition
+#else
     ge K1 = vb_mul(&tk, gamma, true);
+#endif
     K1 = fb_accumulate(K1, C->fb[ACT_BASE_H2], k_bar, false);
     K1 = fb_accumulate(K1, C->fb[ACT_BASE_H3], r_bar, false);
     {
@@ -788,7 +814,7 @@ ACT_FN void spend_head_thread(const act_ctx* C, size_t p, const u32* proofs, u32
     }
     {
         // A2 = B*r3_bar + h1*c_bar + h3*r_bar - (G + h2*k)*gamma                          (:792,796-799)
-        ge A2 = vb_mul(&t[1], r3_bar, false);
+        ge A2 = vb_mul_pub(&t[1], r3_bar, false);
         A2 = fb_accumulate(A2, C->fb[ACT_BASE_H1], c_bar, false);
         A2 = fb_accumulate(A2, C->fb[ACT_BASE_H3], r_bar, false);
         A2 = fb_accumulate(A2, C->fb[ACT_BASE_G], gamma, true);
@@ -809,7 +835,7 @@ ACT_FN void spend_head_thread(const act_ctx* C, size_t p, const u32* proofs, u32
     {
         // C = h1*(-c_bar) + h2*k_bar + h3*s_bar - (h1*s + K')*gamma                       (:825-829)
         vb_table_build(&t[0], Kp);
-        ge Cc = vb_mul(&t[0], gamma, true);
+        ge Cc = vb_mul_pub(&t[0], gamma, true);
         Cc = fb_accumulate(Cc, C->fb[ACT_BASE_H1], sc_add(c_bar, sc_mul(s, gamma)), true);
         Cc = fb_accumulate(Cc, C->fb[ACT_BASE_H2], k_bar, false);
         Cc = fb_accumulate(Cc, C->fb[ACT_BASE_H3], s_bar, false);
