@@ -808,7 +808,7 @@ ACT_FN void spend_head_thread(const act_ctx* C, size_t p, const u32* proofs, u32
                 A1 = ge_dbl(A1, false); A1 = ge_dbl(A1, false); A1 = ge_dbl(A1, false); A1 = ge_dbl(A1, true);
             }
             A1 = ge_add_cached(A1, vb_lookup_ct(&t[0], sc_digit<4>(sa, i)));
-            A1 = ge_add_cached(A1, vb_lookup(&t[1], sc_digit<4>(sb, i), false));
+            A1 = ge_add_cached_u(A1, vb_lookup(&t[1], sc_digit<4>(sb, i), false), 0u, i == 0);   // a doubling follows: no T until the last window
         }
         store_point(it + 24, A1);
     }

@@ -43,7 +43,7 @@ UNIT = "proofs/s"
 #   (profiles/r02f_*.txt): encode 5.40e5 (profiles/r02k_spend_encode_kernel.txt; 6.81e5 before r02j's 64-point batches), head 7.43e5, sign 3.40e5 per proof, issue 5.37e5 per request.  (Round 1's hand counts --
 #   7.1e5 / 8.2e5 / 3.9e5 / 6.0e5 -- were 4-13 % too high; the constants below are what the kernels execute.)
 LIMB_MACS_PER_SPEND_RANGE = 128 * (1266 * 44 + 2525 * 72)      # 3.040e7
-LIMB_MACS_PER_SPEND_HEAD = 7.34e5       # 7.43e5 executed (r02f) - 2 x 63 T products (72 each) that vb_mul_pub no longer computes (r02z)
+LIMB_MACS_PER_SPEND_HEAD = 7.29e5       # 7.43e5 executed (r02f) - 3 x 63 T products (72 each) no longer computed: two vb_mul_pub, the A1 window loop (r02z)
 LIMB_MACS_PER_SPEND_SIGN = 3.40e5
 LIMB_MACS_PER_SPEND_ENCODE = 5.40e5     # executed at 64 points per inversion (profiles/r02k_spend_encode_kernel.txt); 6.81e5 at 16 per inversion (r02f)
 LIMB_MACS_PER_SPEND = LIMB_MACS_PER_SPEND_RANGE + LIMB_MACS_PER_SPEND_ENCODE + LIMB_MACS_PER_SPEND_HEAD + LIMB_MACS_PER_SPEND_SIGN
