@@ -707,8 +707,10 @@ def main():
         eng.close()
         del d_ref, d_nul, d_st, d_rnd, d_tokens
         torch.cuda.empty_cache()
-        time.sleep(5.0)                       # the exited ranks' contexts are torn down by the driver
-        if rank == 0:
+        time.sleep(8.0)                       # the exited ranks' contexts are torn down by the driver
+        box = {}
+
+        def multi_leg():
             try:
                 mp_, mr_, ref0 = m_keep
                 tot = world * nm
@@ -725,19 +727,29 @@ def main():
                         mstep()
                         step_s.append(time.perf_counter() - t0)
                     m_s = sum(step_s)
+                    med = sorted(step_s)[len(step_s) // 2]
                     stv = m_st.numpy()
-                    multi_abi = {"value": tot * msteps / m_s, "unit": UNIT, "n": tot, "steps": msteps, "n_gpus": world, "step_s": [round(t, 4) for t in step_s],
+                    box["r"] = {"value": tot / med, "unit": UNIT, "n": tot, "steps": msteps, "n_gpus": world, "step_s": [round(t, 4) for t in step_s],
+                                 "value_is": "proofs per MEDIAN step (a step now and then is slowed by the tear-down of the exited ranks' contexts)",
+                                 "mean_value": tot * msteps / m_s,
                                  "api": "act_engine_create_multi + act_batch_verify_spend_and_refund_screened: one process, one handle, pinned host buffers, "
                                         "shards over per-device replicas, cudaMemcpyPeerAsync gather of status + nullifiers to replica 0, replay screen",
                                  "accepted": int((stv == 0).sum()), "flagged_replays": int((stv == 3).sum()),
                                  "first_shard_equals_rank0_refunds": bool((m_ref[:nm * 128].numpy() == ref0.numpy()).all()),
                                  "note": "run last, after the other ranks have exited; tools/multi_abi_bench.py measures the same call from a "
                                          "lone process (profiles/r02m_multi_abi.txt)"}
-                    assert multi_abi["first_shard_equals_rank0_refunds"], "multi-device leg differs from the per-rank leg"
+                    assert box["r"]["first_shard_equals_rank0_refunds"], "multi-device leg differs from the per-rank leg"
                     assert int((stv == 0).sum()) == tot, "multi-device leg: a valid unique proof was rejected or flagged"
                 del mp_, mr_, m_ref, m_nul, m_st
+
             except Exception as ex:
-                multi_abi = {"unavailable": repr(ex)}
+                box["r"] = {"unavailable": repr(ex)}
+
+        # under a watchdog: whatever happens in this leg, rank 0 still prints its JSON line
+        th = threading.Thread(target=multi_leg, daemon=True)
+        th.start()
+        th.join(timeout=240.0)
+        multi_abi = box.get("r") or {"unavailable": "the multi-device leg did not finish within 240 s"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
