@@ -26,8 +26,12 @@
  * this oracle is checked (tests/test_oracle_*.py) against RFC 9496 Appendix A vectors,
  * BLAKE3 via the independent python `blake3` package, an independent libsodium
  * ristretto255 + python big-int restatement of the whole issue->spend->refund trip, and
- * the SURVEY.md Appendix C provisional golden trip.  "parity unpinned by the reference's
- * own tests" -- see DESIGN.md.
+ * the SURVEY.md Appendix C provisional golden trip; since round 2 also the WHOLE mutation
+ * corpus and a differential fuzz, item by item, status and output bytes, against that
+ * independent stack.  "parity unpinned by the reference's own tests" -- see DESIGN.md.
+ * The real pin is prepared: rust/golden-dump writes tests/golden/ref_crate.json from the
+ * unmodified crate wherever a Rust toolchain exists, and tests/test_ref_crate_golden.py
+ * replays it through this oracle and through the CUDA engine.
  *
  * Representation here is deliberately different from the GPU code (5x51-bit limbs with
  * unsigned __int128 products vs. 8x32-bit limbs on the device) so that the two
